@@ -1,0 +1,56 @@
+"""Vite binary graph format reader / writer.
+
+Layout (little-endian, no padding; /root/reference/distgraph.cpp:99-100,131,170
+and SURVEY.md A4), 64-bit build: ``int64 nv; int64 ne; int64 offsets[nv+1];
+struct {int64 tail; double weight;} edges[ne]``.  ``ne`` counts directed CSR
+entries.  The reader also implements the reference's vertex-range partition
+(``parts[p] = nv*p // P``, distgraph.cpp:102,118-119) so that rank ``p`` of
+``P`` loads only its rows, with offsets rebased to 0 like distgraph.cpp:194-195.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .graphgen import CSRGraph
+
+_EDGE_DT = np.dtype([("tail", "<i8"), ("weight", "<f8")])
+
+
+def write_vite(path: str, g: CSRGraph) -> None:
+    g = g.cpu()
+    with open(path, "wb") as f:
+        np.array([g.nv, g.ne], dtype="<i8").tofile(f)
+        g.offsets.numpy().astype("<i8", copy=False).tofile(f)
+        edges = np.empty(g.ne, dtype=_EDGE_DT)
+        edges["tail"] = g.tails.numpy()
+        edges["weight"] = g.weights.numpy()
+        edges.tofile(f)
+
+
+def partition_ranges(nv: int, nparts: int) -> list[int]:
+    """parts[p] = nv*p // P (distgraph.cpp:118-119, rebuild.cpp:294-295)."""
+    return [(nv * p) // nparts for p in range(nparts + 1)]
+
+
+def read_vite(path: str, rank: int = 0, nparts: int = 1) -> tuple[CSRGraph, int, int]:
+    """Returns (local rows as a CSRGraph with global tails, base, global nv)."""
+    with open(path, "rb") as f:
+        nv, ne = (int(x) for x in np.fromfile(f, dtype="<i8", count=2))
+        parts = partition_ranges(nv, nparts)
+        base, bound = parts[rank], parts[rank + 1]
+        f.seek(16 + base * 8)
+        offsets = np.fromfile(f, dtype="<i8", count=bound - base + 1)
+        e0, e1 = int(offsets[0]), int(offsets[-1])
+        f.seek(16 + (nv + 1) * 8 + e0 * _EDGE_DT.itemsize)
+        edges = np.fromfile(f, dtype=_EDGE_DT, count=e1 - e0)
+    g = CSRGraph(bound - base, torch.from_numpy(offsets - e0),
+                 torch.from_numpy(np.ascontiguousarray(edges["tail"])),
+                 torch.from_numpy(np.ascontiguousarray(edges["weight"])))
+    return g, base, nv
+
+
+def slice_rows(g: CSRGraph, base: int, bound: int) -> CSRGraph:
+    """Rows [base, bound) of an in-memory graph, offsets rebased, tails global."""
+    e0, e1 = int(g.offsets[base]), int(g.offsets[bound])
+    return CSRGraph(bound - base, g.offsets[base:bound + 1] - e0, g.tails[e0:e1], g.weights[e0:e1])
