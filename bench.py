@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py — edges/sec per Louvain sweep (BASELINE.json metric) on N B200s.
+
+A *step* is one synchronous local-move sweep of phase 0 — neighbour scan +
+per-community accumulation + gain argmax + community-delta commit, followed by
+the community-info apply + modularity reduction (and, at N > 1, the label /
+delta exchange) — on BASELINE.json configs[1]: R-MAT scale-20 (scale-20+log2 N
+at N GPUs: weak scaling, per-GPU work fixed).  Steps walk the real algorithm:
+iteration 1, 2, ... of the phase; when the phase converges (dQ < 1e-6) the
+state is reset to singletons inside the timed region and the walk continues.
+
+  python bench.py --gpus 1 --steps K --warmup W            # this framework
+  python bench.py --impl reference --gpus 1 --steps K ...   # reference CPU path (oracle/_ref)
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "undirected_edges_per_second_per_louvain_sweep"
+UNIT = "edges/s"
+BASE_SCALE = 20  # BASELINE.json configs[1]
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_graph(scale, device, permute):
+    from cuvite_b200 import graphgen as gg
+    return gg.rmat(scale, seed=2, device=device, permute_seed=3 if permute else None)
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU louvain.cpp path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle.binding import Oracle, Reference
+    scale = BASE_SCALE + (args.gpus - 1).bit_length() if args.scale is None else args.scale
+    g = make_graph(scale, "cpu", args.gpus > 1)
+    o, t, w = g.offsets.numpy(), g.tails.numpy(), g.weights.numpy()
+    if Reference.available():
+        impl, kind = Reference(), "reference"
+        h = impl.graph(o, t, w)
+        run = lambda: impl.phase_on(h)  # noqa: E731
+    else:
+        impl, kind = Oracle(), "port"
+        run = lambda: impl.phase(o, t, w)  # noqa: E731
+    cores = impl.num_threads()
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        run()
+    steps, secs, iters = 0, 0.0, 0
+    t_begin = time.perf_counter()
+    while steps < args.steps and (time.perf_counter() - t_begin) < 120.0:
+        p = run()
+        steps += 1
+        secs += p.seconds
+        iters += p.iters
+    value = (g.ne / 2) * iters / secs
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": 1e3 * secs / iters, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"R-MAT scale-{scale} ef16 (a,b,c,d=.57,.19,.19,.05) seed 2, phase-0 sweeps",
+                       "nv": g.nv, "csr_entries": g.ne, "sweeps_timed": iters,
+                       "step": "one full phase-0 run of louvain.cpp (all its sweeps); ms_per_step is per sweep"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{steps} x phase 0 of the same graph ({iters} sweeps)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- own arm, one GPU
+def bench_single(args):
+    import numpy as np
+    import torch
+    from cuvite_b200 import build
+    build.build()
+    from cuvite_b200.engine import GpuGraph, gpu_for_louvain_iteration, gpu_reduce_mod, set_gpuDevices
+    set_gpuDevices(0)
+    torch.cuda.set_device(0)
+    scale = BASE_SCALE if args.scale is None else args.scale
+    g = make_graph(scale, "cuda", False)
+    nv, ne = g.nv, g.ne
+    gpu = GpuGraph()
+    gpu.upload_device(g.offsets, g.tails, g.weights)
+    info = gpu.info()
+
+    # ---- device-resident steps ------------------------------------------------
+    def step(state):
+        gpu.sweep()
+        sums = gpu.apply_and_reduce()
+        q = gpu.modularity_from_sums(sums)
+        state["sweep_ms"].append(gpu.last_sweep_ms())
+        if q - state["prev"] < 1e-6:  # phase converged: restart from singletons (inside the timed region)
+            gpu.phase_reset()
+            state["prev"] = -1.0
+            state["phases"] += 1
+        else:
+            state["prev"] = q
+            gpu.rotate_labels()
+
+    gpu.phase_begin()
+    st = {"prev": -1.0, "sweep_ms": [], "phases": 0}
+    for _ in range(max(args.warmup, 3)):
+        step(st)
+    gpu.phase_reset()
+    st = {"prev": -1.0, "sweep_ms": [], "phases": 0}
+    launches0 = gpu.launch_count
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(st)  # every step ends with a stream synchronise (the 2 sums reach the host)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    launches = gpu.launch_count - launches0
+    ms_per_step = wall_ms / args.steps  # host clock around synchronising steps == device-complete time
+    value = (ne / 2) / (ms_per_step * 1e-3)
+    sweep_ms = statistics.mean(st["sweep_ms"])
+    bytes_sweep = 12 * ne + 40 * nv
+    peak, peak_src = measured_peak_gbs()
+    achieved = bytes_sweep / (sweep_ms * 1e-3) / 1e9
+
+    # ---- end to end through the plugin call with pinned host buffers -----------
+    o_h = g.offsets.cpu().numpy()
+    edges = np.empty(ne, dtype=[("tail", "<i8"), ("weight", "<f8")])
+    edges["tail"] = g.tails.cpu().numpy()
+    edges["weight"] = g.weights.cpu().numpy()
+    edges_pin = torch.from_numpy(edges.view(np.uint8)).pin_memory()
+    edges_p = edges_pin.numpy().view(edges.dtype)
+
+    def pinned(a):
+        return torch.from_numpy(a).pin_memory().numpy()
+
+    vdeg = pinned((g.offsets[1:] - g.offsets[:-1]).double().cpu().numpy())
+    const = 1.0 / float(ne)
+    bufs = {k: pinned(np.zeros(nv, dt)) for k, dt in (("past", np.int64), ("curr", np.int64), ("target", np.int64),
+                                                       ("csize", np.int64), ("usz", np.int64), ("cdeg", np.float64),
+                                                       ("udg", np.float64), ("cw", np.float64))}
+    o_pin = pinned(o_h)
+
+    def e2e_reset():
+        bufs["past"][:] = np.arange(nv)
+        bufs["curr"][:] = bufs["past"]
+        bufs["csize"][:] = 1
+        bufs["cdeg"][:] = vdeg
+
+    def e2e_steps(k):
+        prev, it, uploads = -1.0, 0, 0
+        e2e_reset()
+        for _ in range(k):
+            it += 1
+            uploads += it == 1
+            bufs["cw"][:] = 0  # distCleanCWandCU, louvain.cpp:664
+            bufs["usz"][:] = 0
+            bufs["udg"][:] = 0
+            gpu_for_louvain_iteration(nv, o_pin, edges_p, bufs["curr"], bufs["target"], vdeg, bufs["csize"],
+                                      bufs["cdeg"], bufs["usz"], bufs["udg"], {}, {}, {}, const, bufs["cw"], 0,
+                                      it, gpu)
+            np.add(bufs["csize"], bufs["usz"], out=bufs["csize"])  # distUpdateLocalCinfo
+            np.add(bufs["cdeg"], bufs["udg"], out=bufs["cdeg"])
+            le = gpu_reduce_mod(bufs["cdeg"], bufs["cw"], gpu, nv)
+            q = le[0] * const - le[1] * const * const
+            if q - prev < 1e-6:
+                e2e_reset()
+                prev, it = -1.0, 0
+            else:
+                prev = q
+                bufs["past"], bufs["curr"], bufs["target"] = bufs["curr"], bufs["target"], bufs["past"]
+        return uploads
+
+    e2e_steps(2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    csr_uploads = e2e_steps(args.steps)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_value = (ne / 2) * args.steps / e2e_s
+    # bytes per step: per-iteration arrays every step; the CSR once per phase restart (num_iters == 1)
+    h2d = nv * (8 + 8 + 8) + nv * 16  # plugin inputs + gpu_reduce_mod inputs
+    d2h = nv * (8 + 8 + 16) + 16
+    csr = ne * 16 + (nv + 1) * 8 + nv * 8
+    h2d_step = h2d + csr * csr_uploads / args.steps
+
+    # ---- CPU baseline beside it (bounded sample: phase 0 of the same graph) -----
+    cpu = None
+    try:
+        from oracle.binding import Oracle, Reference
+        t_cpu = g.tails.cpu().numpy()
+        w_cpu = g.weights.cpu().numpy()
+        if Reference.available():
+            R = Reference()
+            h = R.graph(o_h, t_cpu, w_cpu)
+            p = R.phase_on(h)
+            R.destroy(h)
+            kind, cores = "reference", R.num_threads()
+        else:
+            O = Oracle()
+            p = O.phase(o_h, t_cpu, w_cpu)
+            kind, cores = "port", O.num_threads()
+        cpu = {"value": (ne / 2) * p.iters / p.seconds, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"1 x phase 0 of the same graph ({p.iters} sweeps, {p.seconds:.2f} s)", "q": p.q}
+    except Exception as ex:  # the checker is optional for the number itself
+        cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 weights / f64 gains" if info.weight_mode == 1 else "f64",
+            "data": "synthetic",
+            "config": {"workload": f"R-MAT scale-{scale} ef16 (a,b,c,d=.57,.19,.19,.05) seed 2, phase-0 sweeps, "
+                                   "single local-move sweep per step", "nv": nv, "csr_entries": ne,
+                       "undirected_edges": ne // 2, "parallelism": "1 GPU",
+                       "l2": "inputs (8 B x entries = %d MB) larger than the 126 MB L2; no flush" % (8 * ne >> 20),
+                       "sweep_kernels_ms": sweep_ms, "first_sweep_ms": st["sweep_ms"][0],
+                       "phase_restarts_in_timed_region": st["phases"],
+                       "classes": {n: int(info.class_count[i]) for i, n in
+                                   enumerate(["deg0", "g4", "g8", "g16", "g32", "w256", "w1k", "b4k", "b16k", "giant"])}},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "sweep kernel group (all degree-class kernels of one sweep), 12E+40V bytes"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
+                    "d2h_bytes_per_step": int(d2h),
+                    "api": "gpu_for_louvain_iteration + gpu_reduce_mod (plugin calls, pinned host buffers)"},
+            "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    gpu.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuvite_b200", choices=["cuvite_b200", "reference"])
+    ap.add_argument("--scale", type=int, default=None, help="override the R-MAT scale (debug)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        return bench_single(args)
+    from cuvite_b200 import dist
+    return dist.bench_multi(args, METRIC, UNIT, BASE_SCALE, measured_peak_gbs, ClockSampler)
+
+
+if __name__ == "__main__":
+    main()

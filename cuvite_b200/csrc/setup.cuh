@@ -1,0 +1,362 @@
+// setup.cuh — per-phase setup kernels (layout conversion, vertex degrees, degree
+// classes), the community-info apply + modularity reduction, and the small
+// scatter/gather helpers of the per-iteration boundary call.
+#pragma once
+
+#include "common.cuh"
+
+namespace cvb {
+
+// Interface layout of one CSR entry: the reference's Edge{GraphElem tail;
+// GraphWeight weight} in its 64-bit build (edge.hpp:22-30).
+struct EdgeAoS {
+  int64_t tail;
+  double weight;
+};
+
+// ---- weight statistics: can the graph use the exact uint32 mode? ----------
+// flags[0] |= 1 when some weight is negative, non-integer or >= 2^32;
+// sum += all weights (double; only compared against 2^32, so the atomic
+// order does not matter).
+template <bool AOS>
+__global__ void k_weight_stats(const void *__restrict__ src, int64_t ne, int *flags, double *sum) {
+  double local = 0.0;
+  int bad = 0;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < ne;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double w = AOS ? static_cast<const EdgeAoS *>(src)[e].weight : static_cast<const double *>(src)[e];
+    if (!(w >= 0.0) || w >= 4294967296.0 || w != floor(w)) bad = 1;
+    local += w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  bad = __any_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (bad) atomicOr(flags, 1);
+    atomicAdd(sum, local);
+  }
+}
+
+// ---- boundary layout -> device layout --------------------------------------
+template <bool AOS, typename W>
+__global__ void k_convert_edges(const void *__restrict__ aos, const int64_t *__restrict__ tails64,
+                                const double *__restrict__ w64, int64_t ne, vid_t *__restrict__ tails,
+                                W *__restrict__ weights) {
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < ne;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t t;
+    double w;
+    if (AOS) {
+      const EdgeAoS x = static_cast<const EdgeAoS *>(aos)[e];
+      t = x.tail;
+      w = x.weight;
+    } else {
+      t = tails64[e];
+      w = w64[e];
+    }
+    tails[e] = static_cast<vid_t>(t);
+    weights[e] = static_cast<W>(w);
+  }
+}
+
+template <typename T64, typename T32>
+__global__ void k_narrow(const T64 *__restrict__ src, T32 *__restrict__ dst, int64_t n, int64_t add) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = static_cast<T32>(src[i] + add);
+}
+
+template <typename T32, typename T64>
+__global__ void k_widen(const T32 *__restrict__ src, T64 *__restrict__ dst, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = static_cast<T64>(src[i]);
+}
+
+// ---- distSumVertexDegree (louvain.cpp:2126-2151) ----------------------------
+// uint32 mode: one warp per vertex, any order is exact.  double mode: one
+// thread per vertex adds in edge order, exactly like the reference's loop.
+template <typename W>
+__global__ void k_vertex_degree(const eid_t *__restrict__ offsets, const W *__restrict__ weights, int64_t nv,
+                                double *__restrict__ vdeg);
+
+template <>
+__global__ void k_vertex_degree<uint32_t>(const eid_t *__restrict__ offsets, const uint32_t *__restrict__ weights,
+                                          int64_t nv, double *__restrict__ vdeg) {
+  const int64_t v = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  if (v >= nv) return;
+  const eid_t e0 = offsets[v], e1 = offsets[v + 1];
+  unsigned long long local = 0;
+  for (eid_t e = e0 + lane; e < e1; e += 32) local += weights[e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if (lane == 0) vdeg[v] = static_cast<double>(local);
+}
+
+template <>
+__global__ void k_vertex_degree<double>(const eid_t *__restrict__ offsets, const double *__restrict__ weights,
+                                        int64_t nv, double *__restrict__ vdeg) {
+  const int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  double tw = 0.0;
+  for (eid_t e = offsets[v]; e < offsets[v + 1]; ++e) tw += weights[e];
+  vdeg[v] = tw;
+}
+
+// Deterministic sum of a double array (fixed grid, block partials, last block
+// adds them in block order).
+__global__ void __launch_bounds__(512) k_sum_f64(const double *__restrict__ x, int64_t n,
+                                                 double *__restrict__ partials, unsigned int *__restrict__ ticket,
+                                                 double *__restrict__ out) {
+  __shared__ double sh[16];
+  __shared__ bool last;
+  double s = 0.0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    s += x[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double b = 0.0;
+    for (int w = 0; w < 16; ++w) b += sh[w];
+    partials[blockIdx.x] = b;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(&partials[b]);
+    out[0] = t;
+    *ticket = 0;
+  }
+}
+
+// ---- degree classes: stable partition of the local vertex ids --------------
+constexpr int kClassBlock = 256;
+
+__global__ void __launch_bounds__(kClassBlock) k_class_count(const eid_t *__restrict__ offsets, int64_t nv,
+                                                            int32_t *__restrict__ block_counts,
+                                                            unsigned long long *__restrict__ class_entries,
+                                                            unsigned long long *__restrict__ max_degree) {
+  __shared__ int cnt[kNumClasses];
+  __shared__ unsigned long long ent[kNumClasses];
+  __shared__ unsigned long long maxd;
+  if (threadIdx.x < kNumClasses) {
+    cnt[threadIdx.x] = 0;
+    ent[threadIdx.x] = 0;
+  }
+  if (threadIdx.x == 0) maxd = 0;
+  __syncthreads();
+  const int64_t v = static_cast<int64_t>(blockIdx.x) * kClassBlock + threadIdx.x;
+  if (v < nv) {
+    const int64_t deg = offsets[v + 1] - offsets[v];
+    const int c = degree_class(deg);
+    atomicAdd(&cnt[c], 1);
+    atomicAdd(&ent[c], static_cast<unsigned long long>(deg));
+    atomicMax(&maxd, static_cast<unsigned long long>(deg));
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumClasses) {
+    block_counts[static_cast<int64_t>(blockIdx.x) * kNumClasses + threadIdx.x] = cnt[threadIdx.x];
+    if (ent[threadIdx.x]) atomicAdd(&class_entries[threadIdx.x], ent[threadIdx.x]);
+  }
+  if (threadIdx.x == 0 && maxd) atomicMax(max_degree, maxd);
+}
+
+// Single block: exclusive scan of block_counts in class-major order.
+// class_start[c] = first list position of class c; block_counts[b][c] becomes
+// the list position where block b's class-c vertices start.
+__global__ void __launch_bounds__(1024) k_class_scan(int32_t *__restrict__ block_counts, int64_t nblocks,
+                                                    int64_t *__restrict__ class_start) {
+  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int c = 0; c < kNumClasses; ++c) {
+    if (threadIdx.x == 0) class_start[c] = carry;
+    for (int64_t b0 = 0; b0 < nblocks; b0 += 1024) {
+      const int64_t b = b0 + threadIdx.x;
+      const int64_t x = (b < nblocks) ? block_counts[b * kNumClasses + c] : 0;
+      int64_t incl = x;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += y;
+      }
+      if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+      __syncthreads();
+      int64_t wbase = 0;
+      for (int w = 0; w < (threadIdx.x >> 5); ++w) wbase += warp_tot[w];
+      const int64_t excl = carry + wbase + incl - x;
+      if (b < nblocks) block_counts[b * kNumClasses + c] = static_cast<int32_t>(excl);
+      __syncthreads();
+      if (threadIdx.x == 1023) carry = excl + x;
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) class_start[kNumClasses] = carry;
+}
+
+__global__ void __launch_bounds__(kClassBlock) k_class_scatter(const eid_t *__restrict__ offsets, int64_t nv,
+                                                              const int32_t *__restrict__ block_offsets,
+                                                              vid_t *__restrict__ list) {
+  __shared__ int warp_cnt[kClassBlock / 32][kNumClasses];
+  const int64_t v = static_cast<int64_t>(blockIdx.x) * kClassBlock + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = threadIdx.x >> 5;
+  const int c = (v < nv) ? degree_class(offsets[v + 1] - offsets[v]) : -1;
+  int rank_in_warp = 0;
+  for (int k = 0; k < kNumClasses; ++k) {
+    const unsigned b = __ballot_sync(0xffffffffu, c == k);
+    if (c == k) rank_in_warp = __popc(b & ((1u << lane) - 1u));
+    if (lane == 0) warp_cnt[wib][k] = __popc(b);
+  }
+  __syncthreads();
+  if (c >= 0) {
+    int before = 0;
+    for (int w = 0; w < wib; ++w) before += warp_cnt[w][c];
+    list[block_offsets[static_cast<int64_t>(blockIdx.x) * kNumClasses + c] + before + rank_in_warp] =
+        static_cast<vid_t>(v);
+  }
+}
+
+// ---- distInitLouvain / distInitComm (louvain.cpp:2103-2124, 2569-2586) ------
+__global__ void k_phase_init_local(int64_t nv_local, vid_t base, vid_t *__restrict__ l0, vid_t *__restrict__ l1,
+                                   vid_t *__restrict__ l2, double *__restrict__ cw) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv_local;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const vid_t id = static_cast<vid_t>(i) + base;
+    l0[i] = id;
+    l1[i] = id;
+    l2[i] = id;
+    cw[i] = 0.0;
+  }
+}
+
+// Community arrays are replicated over all nv_global ids.  `vdeg_global` is
+// the vertex degree of every global vertex (one GPU: the local array).
+__global__ void k_phase_init_global(int64_t nv_global, const double *__restrict__ vdeg_global,
+                                    vid_t *__restrict__ labels_global, double *__restrict__ cdeg,
+                                    int32_t *__restrict__ csize, double *__restrict__ ddeg,
+                                    int32_t *__restrict__ dsize) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv_global;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (labels_global) labels_global[i] = static_cast<vid_t>(i);
+    if (vdeg_global) cdeg[i] = vdeg_global[i];
+    csize[i] = 1;
+    ddeg[i] = 0.0;
+    dsize[i] = 0;
+  }
+}
+
+// ---- distUpdateLocalCinfo + distComputeModularity ---------------------------
+// (louvain.cpp:2539-2552, 2433-2481; modularity.cu:36-100).  One streaming
+// pass: Cinfo += delta and delta = 0 over [0, nv_global); a2 = sum degree^2
+// over the owned communities [own0, own1); e = sum clusterWeight over the
+// local vertices.  Two-level deterministic reduction: fixed grid, per-block
+// partials, the last block to finish adds them in block order.
+constexpr int kReduceBlock = 512;
+
+__global__ void __launch_bounds__(kReduceBlock) k_apply_reduce(int64_t nv_global, int64_t own0, int64_t own1,
+                                                              int64_t nv_local, double *__restrict__ cdeg,
+                                                              int32_t *__restrict__ csize,
+                                                              double *__restrict__ ddeg, int32_t *__restrict__ dsize,
+                                                              const double *__restrict__ cw,
+                                                              double *__restrict__ partials,
+                                                              unsigned int *__restrict__ ticket,
+                                                              double *__restrict__ out) {
+  __shared__ double sh_e[kReduceBlock / 32], sh_a[kReduceBlock / 32];
+  __shared__ bool last;
+  double e = 0.0, a2 = 0.0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (int64_t c = t0; c < nv_global; c += stride) {
+    const double dd = ddeg[c];
+    const int32_t ds = dsize[c];
+    double d = cdeg[c];
+    if (dd != 0.0 || ds != 0) {
+      d += dd;
+      cdeg[c] = d;
+      csize[c] += ds;
+      ddeg[c] = 0.0;
+      dsize[c] = 0;
+    }
+    if (c >= own0 && c < own1) a2 += d * d;
+  }
+  for (int64_t i = t0; i < nv_local; i += stride) e += cw[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh_e[threadIdx.x >> 5] = e;
+    sh_a[threadIdx.x >> 5] = a2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double be = 0.0, ba = 0.0;
+    for (int w = 0; w < kReduceBlock / 32; ++w) {
+      be += sh_e[w];
+      ba += sh_a[w];
+    }
+    partials[2 * blockIdx.x] = be;
+    partials[2 * blockIdx.x + 1] = ba;
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double te = 0.0, ta = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) {
+      te += __ldcg(&partials[2 * b]);
+      ta += __ldcg(&partials[2 * b + 1]);
+    }
+    out[0] = te;
+    out[1] = ta;
+    *ticket = 0;
+  }
+}
+
+// ---- boundary-call helpers ---------------------------------------------------
+__global__ void k_scatter_labels(int64_t n, const int64_t *__restrict__ idx, const int64_t *__restrict__ val,
+                                 vid_t *__restrict__ dst) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[idx[i]] = static_cast<vid_t>(val[i]);
+}
+
+__global__ void k_scatter_cinfo(int64_t n, const int64_t *__restrict__ idx, const int64_t *__restrict__ size,
+                                const double *__restrict__ deg, int64_t add, int32_t *__restrict__ csize,
+                                double *__restrict__ cdeg) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t c = idx ? idx[i] : i + add;
+    csize[c] = static_cast<int32_t>(size[i]);
+    cdeg[c] = deg[i];
+  }
+}
+
+// out_size/out_deg[i] = delta at community idx[i] (or add+i); the delta is
+// cleared afterwards so the arrays are zero for the next call.
+__global__ void k_gather_deltas(int64_t n, const int64_t *__restrict__ idx, int64_t add,
+                                double *__restrict__ ddeg, int32_t *__restrict__ dsize,
+                                int64_t *__restrict__ out_size, double *__restrict__ out_deg) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t c = idx ? idx[i] : i + add;
+    out_size[i] = dsize[c];
+    out_deg[i] = ddeg[c];
+    dsize[c] = 0;
+    ddeg[c] = 0.0;
+  }
+}
+
+}  // namespace cvb

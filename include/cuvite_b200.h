@@ -1,0 +1,232 @@
+/* cuvite_b200.h — C ABI of the B200-native Louvain local-move engine.
+ *
+ * Drop-in scope: the GPU offload library of pnnl/cuVite ("cuda_louvain":
+ * louvain_cuda.cu, modularity.cu, GpuGraph.cu) and the GPU overload of the
+ * phase loop that calls it.  Each entry point cites the reference interface it
+ * replaces (paths relative to the reference tree).  Plain pointers and sizes
+ * only; ids are int64 and weights are double at this boundary, exactly the
+ * reference's 64-bit build (edge.hpp:15-19).  The C++ source-level adapter that
+ * re-creates the reference's own symbols (CuVite::GpuGraph,
+ * gpu_for_louvain_iteration, gpu_reduce_mod, set_gpuDevices,
+ * distLouvainMethod(..., GpuGraph&)) on top of this ABI is
+ * include/GpuGraph.cuh + cuvite_b200/csrc/adapter.cpp; see INTEGRATION.md.
+ *
+ * Error model: every int-returning function returns 0 on success and a
+ * negative cvb_status otherwise; cvb_last_error() gives the message.  (The
+ * reference printf()s and exit(1)s on any CUDA error, GpuGraph.cuh:23; the
+ * C++ adapter reproduces that on a non-zero status.)  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails.
+ *
+ * Threading: an engine is used from one host thread at a time (the reference
+ * calls its GPU library from the rank's main thread, louvain.cpp:665).
+ */
+#ifndef CUVITE_B200_H
+#define CUVITE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cvb_engine cvb_engine;
+
+typedef enum {
+  CVB_OK = 0,
+  CVB_ERR_CUDA = -1,      /* a CUDA runtime call failed */
+  CVB_ERR_ARG = -2,       /* invalid argument / call order */
+  CVB_ERR_CAPACITY = -3,  /* graph exceeds a 32-bit device id / offset limit */
+  CVB_ERR_STATE = -4      /* engine not in the state the call needs */
+} cvb_status;
+
+/* Arithmetic mode chosen per graph at upload (cvb_graph_info.weight_mode). */
+enum { CVB_WEIGHTS_U32 = 1 /* all weights non-negative integers, total < 2^32: exact */,
+       CVB_WEIGHTS_F64 = 2 /* arbitrary doubles */ };
+
+const char *cvb_last_error(void);
+const char *cvb_version(void);
+
+/* Number of visible CUDA devices (0 when there is none; never fails). */
+int cvb_device_count(void);
+
+/* Replaces set_gpuDevices(int *me) — louvain_cuda.cu:1634-1669, declared
+ * louvain.hpp:249, called main.cpp:73: bind this process to device
+ * local_rank % ndev.  (The reference derives the node-local rank from
+ * MPI_Comm_split_type; here the launcher's LOCAL_RANK is passed in.) */
+int cvb_set_device(int local_rank);
+
+/* Replaces the CuVite::GpuGraph constructor + devMemAllocate() +
+ * pinnedAndDevMemAllocate() — GpuGraph.cuh:38-45, GpuGraph.cu:9-101, called
+ * main.cpp:209-211.  Buffers are sized lazily per graph, grown never shrunk,
+ * and freed by cvb_destroy (the reference never frees).  `stream` is a
+ * cudaStream_t (0 = the engine creates its own). */
+cvb_engine *cvb_create(void *stream);
+void cvb_destroy(cvb_engine *e);
+
+/* ---- graph upload (once per phase; the reference re-uploads the whole edge
+ * list every iteration, louvain_cuda.cu:2403-2438) ------------------------- */
+
+/* Rows [base, base+nv_local) of a graph with nv_global vertices, Vite CSR
+ * layout in HOST memory: offsets[nv_local+1] rebased to 0 and tails/weights
+ * either as the reference's AoS `Edge{int64 tail; double weight}` array
+ * (edges_aos != NULL; graph.hpp:35-36, edge.hpp:22-30) or as two SoA arrays.
+ * Replaces the flatten + H2D part of gpu_for_louvain_iteration,
+ * louvain_cuda.cu:2244-2438. */
+int cvb_graph_upload_host(cvb_engine *e, int64_t nv_local, int64_t base, int64_t nv_global,
+                          const int64_t *offsets, const void *edges_aos,
+                          const int64_t *tails, const double *weights);
+
+/* Same, from DEVICE memory (direct-to-GPU load path): offsets int64, tails
+ * int64, weights double, all device pointers. */
+int cvb_graph_upload_device(cvb_engine *e, int64_t nv_local, int64_t base, int64_t nv_global,
+                            const int64_t *d_offsets, const int64_t *d_tails,
+                            const double *d_weights);
+
+typedef struct {
+  int64_t nv_local, base, nv_global, ne_local;
+  int32_t weight_mode;        /* CVB_WEIGHTS_* */
+  int32_t num_classes;        /* degree classes in use */
+  int64_t class_count[16];    /* vertices per degree class */
+  int64_t class_entries[16];  /* CSR entries per degree class */
+  int64_t max_degree;
+  double local_weight;        /* sum of local vertex degrees (the 2m share) */
+} cvb_graph_info;
+int cvb_graph_get_info(cvb_engine *e, cvb_graph_info *out);
+
+/* ---- one phase, resident on the device ---------------------------------- */
+
+/* Replaces distInitLouvain — louvain.cpp:2103-2124 (distSumVertexDegree
+ * 2126-2151, distCalcConstantForSecondTerm 2153-2183, distInitComm
+ * 2569-2586): labels = own id, Cinfo = {1, vDegree}, constant = 1/total.
+ * total_weight = the global sum of vertex degrees (pass <= 0 on one GPU to use
+ * the local sum).  On >1 GPU the caller then fills the replicated community
+ * degree array through cvb_buffer (see cuvite_b200/dist.py). */
+int cvb_phase_begin(cvb_engine *e, double total_weight);
+
+/* One synchronous local-move sweep over the local rows: replaces
+ * distCleanCWandCU + the kernels of gpu_for_louvain_iteration
+ * (louvain_cuda.cu:2463-2699) + updateLocalTarget_gpu (49-173); semantics of
+ * distExecuteLouvainIteration (louvain.cpp:2246-2382).  Reads labels/Cinfo of
+ * iteration k, writes target[], clusterWeight[], and ADDS the community
+ * deltas into the (zeroed) delta arrays.  Asynchronous on the engine stream. */
+int cvb_sweep(cvb_engine *e);
+
+/* Replaces distUpdateLocalCinfo (louvain.cpp:2539-2552) + gpu_reduce_mod /
+ * compute_modularity (modularity.cu:36-141): Cinfo += delta (all nv_global
+ * communities), delta = 0, then sums[0] = sum of clusterWeight over local
+ * vertices, sums[1] = sum of degree^2 over the communities this rank owns
+ * ([base, base+nv_local)).  Synchronises the stream; sums is a HOST pointer. */
+int cvb_apply_and_reduce(cvb_engine *e, double sums[2]);
+
+/* Q = e*c - a2*c*c (louvain.cpp:2472-2473) from globally reduced sums. */
+double cvb_modularity_from_sums(const cvb_engine *e, const double sums[2]);
+
+/* past <- curr <- target <- past (louvain.cpp:562-567); O(1) pointer rotation. */
+int cvb_rotate_labels(cvb_engine *e);
+
+/* Whole phase on one GPU: replaces distLouvainMethod(..., GpuGraph&) —
+ * louvain.hpp:93-97, louvain.cpp:591-753, called main.cpp:344.  Returns the
+ * accepted modularity in *q_out, iterations in *iters_out; labels of the last
+ * accepted iteration (cvect = pastComm, louvain.cpp:741) stay on the device
+ * (cvb_get_labels).  max_iters <= 0 means unlimited. */
+int cvb_phase_run(cvb_engine *e, double lower, double thresh, int max_iters,
+                  double *q_out, int *iters_out);
+
+enum { CVB_LABELS_PAST = 0, CVB_LABELS_CURR = 1, CVB_LABELS_TARGET = 2 };
+/* D2H of a local label vector as int64 global ids (host pointer, nv_local). */
+int cvb_get_labels(cvb_engine *e, int which, int64_t *out);
+/* D2H of clusterWeight[nv_local] / community {size,degree}[nv_global]. */
+int cvb_get_cluster_weight(cvb_engine *e, double *out);
+int cvb_get_cinfo(cvb_engine *e, int64_t *size_out, double *degree_out);
+
+/* Reset labels/Cinfo to the start-of-phase state without re-uploading. */
+int cvb_phase_reset(cvb_engine *e);
+
+/* ---- raw device buffers, for NCCL collectives issued by the host side ---- */
+enum {
+  CVB_BUF_LABELS_GLOBAL = 0, /* int32[nv_global] labels every sweep reads          */
+  CVB_BUF_LABELS_CURR = 1,   /* int32[nv_local]                                     */
+  CVB_BUF_LABELS_TARGET = 2, /* int32[nv_local]                                     */
+  CVB_BUF_LABELS_PAST = 3,   /* int32[nv_local]                                     */
+  CVB_BUF_CDEG = 4,          /* double[nv_global] community degree (replicated)     */
+  CVB_BUF_CSIZE = 5,         /* int32[nv_global]  community size   (replicated)     */
+  CVB_BUF_DDEG = 6,          /* double[nv_global] degree deltas of this sweep       */
+  CVB_BUF_DSIZE = 7,         /* int32[nv_global]  size deltas of this sweep         */
+  CVB_BUF_VDEG = 8,          /* double[nv_local]                                    */
+  CVB_BUF_CW = 9,            /* double[nv_local]  clusterWeight                     */
+  CVB_BUF_OFFSETS = 10,      /* int64[nv_local+1]                                   */
+  CVB_BUF_TAILS = 11,        /* int32[ne_local]                                     */
+  CVB_BUF_WEIGHTS = 12       /* uint32 or double [ne_local], see weight_mode        */
+};
+void *cvb_buffer(cvb_engine *e, int which);
+void *cvb_stream(cvb_engine *e);
+int cvb_sync(cvb_engine *e);
+
+/* ---- the reference's per-iteration plugin call, flattened to C ----------- */
+
+/* Replaces gpu_for_louvain_iteration — louvain.hpp:232-245,
+ * louvain_cuda.cu:1671-1686 / 2235-2735, called louvain.cpp:665-668 — with the
+ * STL containers flattened (HOST pointers):
+ *   curr_comm[nv]            currComm (global ids)
+ *   v_degree[nv]             vDegree (read when num_iters == 1)
+ *   local_csize/cdeg[nv]     localCinfo
+ *   n_ghost, ghost_vertex[], ghost_comm[]     remoteComm  (vertex -> community)
+ *   n_rcomm, rcomm_id[], rcomm_size[], rcomm_degree[]   remoteCinfo (ascending id,
+ *                            i.e. std::map order, louvain_cuda.cu:2260-2290)
+ *   constant                 constantForSecondTerm
+ *   num_iters                1-based; 1 => `graph` (offsets/edges) is new and uploaded
+ * outputs:
+ *   target_comm[nv], cluster_weight[nv] (= counter[0], louvain.cpp:2294),
+ *   local_cupd_size/deg[nv]  += deltas (localCupdate),
+ *   rcomm_upd_size/deg[n_rcomm] += deltas (remoteCupdate, same order as rcomm_id).
+ * Returns 1 on success like the reference (louvain_cuda.cu:1685), <= 0 on error. */
+int cvb_louvain_iteration(cvb_engine *e, int64_t nv, int64_t base, int64_t nv_global,
+                          const int64_t *offsets, const void *edges_aos,
+                          const int64_t *curr_comm, const double *v_degree,
+                          const int64_t *local_csize, const double *local_cdeg,
+                          int64_t n_ghost, const int64_t *ghost_vertex, const int64_t *ghost_comm,
+                          int64_t n_rcomm, const int64_t *rcomm_id, const int64_t *rcomm_size,
+                          const double *rcomm_degree, double constant, int num_iters,
+                          int64_t *target_comm, double *cluster_weight,
+                          int64_t *local_cupd_size, double *local_cupd_deg,
+                          int64_t *rcomm_upd_size, double *rcomm_upd_deg);
+
+/* Replaces gpu_reduce_mod — louvain.hpp:247-248, modularity.cu:102-141, called
+ * louvain.cpp:2496: le_la_xx[0] = sum clusterWeight, [1] = sum degree^2 over nv
+ * local entries (HOST pointers). */
+int cvb_reduce_mod(cvb_engine *e, int64_t nv, const double *local_cdeg,
+                   const double *cluster_weight, double le_la_xx[2]);
+
+/* ---- coarsening (rebuild.cpp) and the multi-phase driver (main.cpp) ------ */
+
+/* Replaces distbuildNextLevelGraph on one rank — rebuild.hpp:59,
+ * rebuild.cpp:430-454: renumber the communities of the PAST labels in order of
+ * first appearance (rebuild.cpp:72-85), aggregate edges, emit the CSR sorted by
+ * tail (rebuild.cpp:413-426) and make it the engine's graph.  new_nv_out gets
+ * the number of communities. */
+int cvb_coarsen(cvb_engine *e, int64_t *new_nv_out);
+
+/* D2H of the engine's current graph in the boundary layout (for writing Vite
+ * files / handing the next level back to the reference's DistGraph). */
+int cvb_graph_download(cvb_engine *e, int64_t *offsets, int64_t *tails, double *weights);
+
+/* The default-flag phase driver of main.cpp:218-495 on one GPU: phases with
+ * threshold 1e-6 until a phase gains no more, coarsening in between.
+ * level_q/level_iters (cumulative)/level_nv hold up to max_levels accepted
+ * levels; comm_out[nv0] (may be NULL) receives the composed community of
+ * every original vertex.  Returns the number of accepted levels (>= 0). */
+int cvb_louvain_run(cvb_engine *e, int max_levels, double *level_q, int *level_iters,
+                    int64_t *level_nv, int64_t *comm_out);
+
+/* ---- instrumentation ------------------------------------------------------ */
+/* Kernels launched by this engine since creation (bench.py "gpu_launches"). */
+int64_t cvb_launch_count(const cvb_engine *e);
+/* Device time of the last cvb_sweep's kernels in ms (CUDA events on the engine
+ * stream; valid after a sync).  Returns < 0 when no sweep ran. */
+float cvb_last_sweep_ms(cvb_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUVITE_B200_H */

@@ -1,0 +1,203 @@
+"""Parity of the CUDA path (through the C ABI) against the golden fixtures the
+real reference produced and against the oracle on seeded graphs.  Integer /
+index outputs must be bit-exact; modularity of integer-weight graphs is
+bit-exact too, real-weight graphs within 1e-12 (the north-star bar is 1e-6)."""
+import numpy as np
+import pytest
+from conftest import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _csr(g):
+    return g["offsets"], g["tails"].astype(np.int64), g["weights"]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_sweep_by_sweep_matches_reference(gpu, name):
+    g = load_golden(name)
+    o, t, w = _csr(g)
+    exact = name != "rmat9_realw"
+    gpu.upload(o, t, w)
+    assert gpu.info().weight_mode == (1 if exact else 2)
+    gpu.phase_begin()
+    for k in range(int(g["iters"])):
+        gpu.sweep()
+        assert np.array_equal(gpu.labels(2), g["targets"][k]), f"targetComm differs in iteration {k + 1}"
+        cw = gpu.cluster_weight()
+        if exact:
+            assert np.array_equal(cw, g["cw"][k])
+        else:
+            np.testing.assert_allclose(cw, g["cw"][k], rtol=1e-13, atol=0)
+        sums = gpu.apply_and_reduce()
+        q = gpu.modularity_from_sums(sums)
+        if exact:
+            assert q == g["qs"][k], (k, q, g["qs"][k])
+        else:
+            assert abs(q - g["qs"][k]) < 1e-12
+        size, deg = gpu.cinfo()
+        assert np.array_equal(size, g["csize"][k])
+        if exact:
+            assert np.array_equal(deg, g["cdeg"][k])
+        else:
+            np.testing.assert_allclose(deg, g["cdeg"][k], rtol=1e-12, atol=1e-12)
+        gpu.rotate_labels()
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_phase_matches_reference(gpu, name):
+    from cuvite_b200.engine import distLouvainMethod
+    g = load_golden(name)
+    q, cvect, iters = distLouvainMethod(*_csr(g), -1.0, 1e-6, gpu)
+    assert iters == int(g["iters"])
+    assert np.array_equal(cvect, g["cvect"])
+    if name != "rmat9_realw":
+        assert q == float(g["q"])
+    else:
+        assert abs(q - float(g["q"])) < 1e-12
+
+
+def test_aos_upload_equals_soa(gpu):
+    g = load_golden("rmat10_intw")
+    o, t, w = _csr(g)
+    edges = np.empty(t.size, dtype=[("tail", "<i8"), ("weight", "<f8")])
+    edges["tail"], edges["weight"] = t, w
+    gpu.upload_aos(o, edges)
+    q, iters = gpu.phase_run()
+    assert q == float(g["q"]) and iters == int(g["iters"]) and np.array_equal(gpu.labels(0), g["cvect"])
+
+
+def test_plugin_call_one_rank(gpu, oracle):
+    """gpu_for_louvain_iteration + gpu_reduce_mod driven exactly like louvain.cpp:638-739."""
+    from cuvite_b200.engine import gpu_for_louvain_iteration, gpu_reduce_mod
+    g = load_golden("hub30k")
+    o, t, w = _csr(g)
+    nv = o.size - 1
+    edges = np.empty(t.size, dtype=[("tail", "<i8"), ("weight", "<f8")])
+    edges["tail"], edges["weight"] = t, w
+    vdeg = oracle.vertex_degree(o, w)
+    csize, cdeg = np.ones(nv, np.int64), vdeg.copy()
+    const = 1.0 / vdeg.sum()
+    past, curr, target = np.arange(nv, dtype=np.int64), np.arange(nv, dtype=np.int64), np.empty(nv, np.int64)
+    prev, iters = -1.0, 0
+    while True:
+        iters += 1
+        cw = np.zeros(nv)
+        usz, udg = np.zeros(nv, np.int64), np.zeros(nv)  # distCleanCWandCU
+        assert gpu_for_louvain_iteration(nv, o, edges, curr, target, vdeg, csize, cdeg, usz, udg, {}, {}, {},
+                                         const, cw, 0, iters, gpu) == 1
+        assert np.array_equal(target, g["targets"][iters - 1])
+        assert np.array_equal(cw, g["cw"][iters - 1])
+        csize += usz
+        cdeg += udg  # distUpdateLocalCinfo
+        assert np.array_equal(csize, g["csize"][iters - 1]) and np.array_equal(cdeg, g["cdeg"][iters - 1])
+        le = gpu_reduce_mod(cdeg, cw, gpu, nv)
+        q = le[0] * const - le[1] * const * const
+        assert q == g["qs"][iters - 1]
+        if q - prev < 1e-6:
+            break
+        prev = q
+        past, curr, target = curr, target, past
+    assert iters == int(g["iters"]) and np.array_equal(past, g["cvect"])
+
+
+def test_plugin_call_partitioned_with_ghosts(gpu, oracle):
+    """Three vertex-range partitions, each through the plugin call with its ghost
+    labels / remote community info as maps (fillRemoteCommunities' outputs)."""
+    from cuvite_b200.engine import gpu_for_louvain_iteration
+    g = load_golden("rmat10_intw")
+    o, t, w = _csr(g)
+    nv = o.size - 1
+    vdeg = oracle.vertex_degree(o, w)
+    # state after one reference iteration, so that labels/Cinfo are non-trivial
+    curr = g["targets"][0].astype(np.int64)
+    csize, cdeg = g["csize"][0].astype(np.int64), g["cdeg"][0]
+    const = 1.0 / vdeg.sum()
+    want_t, want_cw, want_dd, want_ds = oracle.sweep(nv, 0, nv, o, t, w, curr, vdeg, cdeg, csize, const)
+    parts = [(nv * p) // 3 for p in range(4)]
+    got_t, got_cw = np.empty(nv, np.int64), np.empty(nv)
+    dd, ds = np.zeros(nv), np.zeros(nv, np.int64)
+    for p in range(3):
+        b0, b1 = parts[p], parts[p + 1]
+        oo = o[b0:b1 + 1] - o[b0]
+        tt, ww = t[o[b0]:o[b1]], w[o[b0]:o[b1]]
+        edges = np.empty(tt.size, dtype=[("tail", "<i8"), ("weight", "<f8")])
+        edges["tail"], edges["weight"] = tt, ww
+        ghosts = np.unique(tt[(tt < b0) | (tt >= b1)])
+        remoteComm = {int(v): int(curr[v]) for v in ghosts}
+        comms = np.unique(np.concatenate([curr[b0:b1], curr[ghosts]]))
+        rc = comms[(comms < b0) | (comms >= b1)]
+        remoteCinfo = {int(c): (int(csize[c]), float(cdeg[c])) for c in rc}
+        remoteCupdate = {int(c): [0, 0.0] for c in rc}
+        tg, cw = np.empty(b1 - b0, np.int64), np.zeros(b1 - b0)
+        usz, udg = np.zeros(b1 - b0, np.int64), np.zeros(b1 - b0)
+        assert gpu_for_louvain_iteration(b1 - b0, oo, edges, curr[b0:b1].copy(), tg, vdeg[b0:b1], csize[b0:b1].copy(),
+                                         cdeg[b0:b1].copy(), usz, udg, remoteComm, remoteCinfo, remoteCupdate,
+                                         const, cw, p, 1, gpu, base=b0, nv_global=nv) == 1
+        got_t[b0:b1], got_cw[b0:b1] = tg, cw
+        ds[b0:b1] += usz
+        dd[b0:b1] += udg
+        for c, (s, d) in remoteCupdate.items():
+            ds[c] += s
+            dd[c] += d
+    assert np.array_equal(got_t, want_t) and np.array_equal(got_cw, want_cw)
+    assert np.array_equal(ds, want_ds) and np.array_equal(dd, want_dd)
+
+
+@pytest.mark.parametrize("scale", [16, 18])
+def test_rmat_phase_matches_oracle(gpu, oracle, scale):
+    from cuvite_b200 import graphgen as gg
+    g = gg.rmat(scale, seed=2)
+    o, t, w = g.offsets.numpy(), g.tails.numpy(), g.weights.numpy()
+    want = oracle.phase(o, t, w, trace=3)
+    gpu.upload(o, t, w)
+    gpu.phase_begin()
+    for k in range(min(3, want.iters)):
+        gpu.sweep()
+        assert np.array_equal(gpu.labels(2), want.targets[k])
+        sums = gpu.apply_and_reduce()
+        assert gpu.modularity_from_sums(sums) == want.qs[k]
+        gpu.rotate_labels()
+    q, iters = gpu.phase_run()
+    assert (q, iters) == (want.q, want.iters)
+    assert np.array_equal(gpu.labels(0), want.cvect)
+
+
+def test_full_size_properties_rmat20(gpu):
+    """BASELINE config C2 size: invariants that need no oracle (conservation of
+    community size/degree, zero-sum deltas, targets drawn from the neighbourhood)."""
+    import torch
+    from cuvite_b200 import graphgen as gg
+    g = gg.rmat(20, seed=2, device="cuda")
+    gpu.upload_device(g.offsets, g.tails, g.weights)
+    info = gpu.info()
+    assert info.nv_local == 1 << 20 and info.weight_mode == 1 and info.local_weight == g.ne
+    assert sum(info.class_count[:info.num_classes]) == info.nv_local
+    assert sum(info.class_entries[:info.num_classes]) == g.ne
+    gpu.phase_begin()
+    labels = torch.arange(g.nv, device="cuda")
+    src = torch.repeat_interleave(torch.arange(g.nv, device="cuda"), g.offsets[1:] - g.offsets[:-1])
+    for _ in range(3):
+        gpu.sweep()
+        gpu.sync()
+        dsize = torch.as_tensor(gpu.buffer("dsize"), device="cuda")
+        ddeg = torch.as_tensor(gpu.buffer("ddeg"), device="cuda")
+        assert int(dsize.sum()) == 0 and float(ddeg.sum()) == 0.0
+        target = torch.as_tensor(gpu.buffer("labels_target"), device="cuda").long()
+        # every target is the own community or the community of a neighbour
+        ok = torch.zeros(g.nv, dtype=torch.bool, device="cuda")
+        ok |= target == labels
+        hit = labels[g.tails] == target[src]
+        ok.index_put_((src[hit],), torch.ones((), dtype=torch.bool, device="cuda"))
+        assert bool(ok.all())
+        sums = gpu.apply_and_reduce()
+        csize = torch.as_tensor(gpu.buffer("csize"), device="cuda")
+        cdeg = torch.as_tensor(gpu.buffer("cdeg"), device="cuda")
+        assert int(csize.sum()) == g.nv and float(cdeg.sum()) == float(g.ne)
+        assert int((csize < 0).sum()) == 0
+        # community info recomputed from the labels equals the incrementally updated one
+        deg = (g.offsets[1:] - g.offsets[:-1]).double()
+        assert torch.equal(torch.zeros(g.nv, dtype=torch.float64, device="cuda").index_add_(0, target, deg), cdeg)
+        assert 0.0 <= sums[0] <= g.ne
+        gpu.rotate_labels()
+        labels = target
