@@ -142,7 +142,7 @@ def bench_single(args):
     import torch
     from cuvite_b200 import build
     build.build()
-    from cuvite_b200.engine import GpuGraph, gpu_for_louvain_iteration, gpu_reduce_mod, set_gpuDevices
+    from cuvite_b200.engine import CLASS_NAMES, GpuGraph, gpu_for_louvain_iteration, gpu_reduce_mod, set_gpuDevices
     set_gpuDevices(0)
     torch.cuda.set_device(0)
     scale = BASE_SCALE if args.scale is None else args.scale
@@ -283,7 +283,7 @@ def bench_single(args):
                        "sweep_kernels_ms": sweep_ms, "first_sweep_ms": st["sweep_ms"][0],
                        "phase_restarts_in_timed_region": st["phases"],
                        "classes": {n: int(info.class_count[i]) for i, n in
-                                   enumerate(["deg0", "g4", "g8", "g16", "g32", "w256", "w1k", "b4k", "b16k", "giant"])}},
+                                   enumerate(CLASS_NAMES[:info.num_classes])}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "kernel": "sweep kernel group (all degree-class kernels of one sweep), 12E+40V bytes"},

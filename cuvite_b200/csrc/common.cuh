@@ -47,17 +47,21 @@ constexpr vid_t kEmptyKey = -1;
 
 // Degree classes.  Boundaries are inclusive upper degrees.
 enum : int {
-  kClsZero = 0,   // deg == 0: never moves, no work
-  kClsG4 = 1,     // 1..4     4 lanes / vertex, single batch, no table
-  kClsG8 = 2,     // 5..8     8 lanes
-  kClsG16 = 3,    // 9..16    16 lanes
-  kClsG32 = 4,    // 17..32   32 lanes
-  kClsW256 = 5,   // 33..128  warp / vertex, 256-slot warp-private table
-  kClsW1K = 6,    // 129..512 warp / vertex, 1024-slot warp-private table
-  kClsB4K = 7,    // 513..2048  block / vertex, 4096-slot shared table
-  kClsB16K = 8,   // 2049..8192 block / vertex, 16384-slot shared table
-  kClsGiant = 9,  // > 8192   block / vertex, table in global memory
-  kNumClasses = 10
+  kClsZero = 0,  // deg == 0: never moves, no work
+  kClsG4 = 1,    // 1..4      one thread / vertex (u32) or 4 lanes / vertex (f64)
+  kClsG8 = 2,    // 5..8      8 lanes / vertex, single batch, no table
+  kClsG16 = 3,   // 9..16     16 lanes
+  kClsG32 = 4,   // 17..32    32 lanes
+  kClsH128 = 5,  // 33..64    hash classes: table capacity = 2 x upper degree
+  kClsH256 = 6,  // 65..128
+  kClsH512 = 7,  // 129..256
+  kClsH1K = 8,   // 257..512
+  kClsH2K = 9,   // 513..1024
+  kClsH4K = 10,  // 1025..2048
+  kClsH8K = 11,  // 2049..4096
+  kClsH16K = 12, // 4097..8192
+  kClsGiant = 13,  // > 8192   tables in global memory
+  kNumClasses = 14
 };
 
 __host__ __device__ inline int degree_class(int64_t deg) {
@@ -66,10 +70,14 @@ __host__ __device__ inline int degree_class(int64_t deg) {
   if (deg <= 8) return kClsG8;
   if (deg <= 16) return kClsG16;
   if (deg <= 32) return kClsG32;
-  if (deg <= 128) return kClsW256;
-  if (deg <= 512) return kClsW1K;
-  if (deg <= 2048) return kClsB4K;
-  if (deg <= 8192) return kClsB16K;
+  if (deg <= 64) return kClsH128;
+  if (deg <= 128) return kClsH256;
+  if (deg <= 256) return kClsH512;
+  if (deg <= 512) return kClsH1K;
+  if (deg <= 1024) return kClsH2K;
+  if (deg <= 2048) return kClsH4K;
+  if (deg <= 4096) return kClsH8K;
+  if (deg <= 8192) return kClsH16K;
   return kClsGiant;
 }
 

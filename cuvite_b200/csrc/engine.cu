@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "setup.cuh"
 #include "sweep.cuh"
+#include "sweep_u32.cuh"
 
 namespace cvb {
 
@@ -114,6 +115,16 @@ struct cvb_engine {
   int giant_blocks = 0;
   size_t giant_stride = 0;
 
+  // CVB_WEIGHTS_U32 fast path
+  DevBuf<uint2> packed;                 // [nv_global] {label|singleton bit, community degree}
+  DevBuf<int64_t> giant_layout;         // chunk_start[ng+1], table_start[ng+1]
+  DevBuf<uint32_t> gkeys, gwts, gays, gmeta, gpiece_key;
+  DevBuf<double> gpiece_gain;
+  int64_t giant_chunks = 0, giant_slots = 0;
+  static constexpr int kAux = 4;
+  cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr, nullptr};
+
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool sweep_timed = false;
@@ -188,15 +199,115 @@ int launch_sweep(cvb_engine *e) {
     k_sweep_group<32, W><<<static_cast<int>((n * 32 + 255) / 256), 256, 0, e->stream>>>(p, lst(kClsG32), (int)n);
     e->launches++;
   }
-  if ((n = cnt(kClsW256)) > 0) CVB_TRY((launch_warp<W, 256>(e, p, lst(kClsW256), n)));
-  if ((n = cnt(kClsW1K)) > 0) CVB_TRY((launch_warp<W, 1024>(e, p, lst(kClsW1K), n)));
-  if ((n = cnt(kClsB4K)) > 0) CVB_TRY((launch_block<W, 4096, 256>(e, p, lst(kClsB4K), n)));
-  if ((n = cnt(kClsB16K)) > 0) CVB_TRY((launch_block<W, 16384, 1024>(e, p, lst(kClsB16K), n)));
+  // adjacent classes are contiguous in the list, so two classes go out in one launch
+  auto cnt2 = [&](int c) { return e->class_start[c + 2] - e->class_start[c]; };
+  if ((n = cnt2(kClsH128)) > 0) CVB_TRY((launch_warp<W, 256>(e, p, lst(kClsH128), n)));
+  if ((n = cnt2(kClsH512)) > 0) CVB_TRY((launch_warp<W, 1024>(e, p, lst(kClsH512), n)));
+  if ((n = cnt2(kClsH2K)) > 0) CVB_TRY((launch_block<W, 4096, 256>(e, p, lst(kClsH2K), n)));
+  if ((n = cnt2(kClsH8K)) > 0) CVB_TRY((launch_block<W, 16384, 1024>(e, p, lst(kClsH8K), n)));
   if ((n = cnt(kClsGiant)) > 0) {
     const int grid = static_cast<int>(n < e->giant_blocks ? n : e->giant_blocks);
     k_sweep_block<W, 1024, 1024, true><<<grid, 1024, 0, e->stream>>>(p, lst(kClsGiant), (int)n, e->giant.p,
                                                                     e->giant_stride, e->giant_log2cap);
     e->launches++;
+  }
+  CVB_CUDA(cudaGetLastError());
+  return CVB_OK;
+}
+
+template <int TPV, int KC, int NCH, int CAP, int VPB>
+int launch_hash(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const vid_t *list, int64_t n,
+                int blocks_per_sm) {
+  const size_t smem = hash_table_bytes<CAP>() * VPB;
+  static bool configured = false;
+  if (!configured) {
+    CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_hash<TPV, KC, NCH, CAP, VPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    configured = true;
+  }
+  int64_t grid = (n + VPB - 1) / VPB;
+  const int64_t cap = static_cast<int64_t>(e->num_sms) * blocks_per_sm;
+  if (grid > cap) grid = cap;
+  k_sweep_u32_hash<TPV, KC, NCH, CAP, VPB><<<static_cast<int>(grid), TPV * VPB, smem, st>>>(p, list, static_cast<int>(n));
+  e->launches++;
+  return CVB_OK;
+}
+
+// The CVB_WEIGHTS_U32 sweep: pack labels, then the degree-class kernels forked
+// over the auxiliary streams and joined back on the engine stream.
+int launch_sweep_u32(cvb_engine *e) {
+  cudaStream_t st = e->stream;
+  k_pack_labels<<<grid_for(e->nvg, 256), 256, 0, st>>>(e->nvg, e->sweep_labels(), e->cdeg.p, e->csize.p,
+                                                       e->packed.p);
+  e->launches++;
+  SweepU32Params p;
+  p.offsets = e->offsets.p;
+  p.tails = e->tails.p;
+  p.weights = reinterpret_cast<const uint32_t *>(e->weights.p);
+  p.packed = e->packed.p;
+  p.vdeg = e->vdeg.p;
+  p.constant = e->constant;
+  p.base = static_cast<vid_t>(e->base);
+  p.target = e->lab[e->targ].p;
+  p.cw = e->cw.p;
+  p.ddeg = e->ddeg.p;
+  p.dsize = e->dsize.p;
+  auto cnt = [&](int c) { return e->class_start[c + 1] - e->class_start[c]; };
+  auto lst = [&](int c) { return e->list.p + e->class_start[c]; };
+  CVB_CUDA(cudaEventRecord(e->ev_fork, st));
+  for (int i = 0; i < cvb_engine::kAux; ++i) CVB_CUDA(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
+  int64_t n;
+  // stream 0: the block-level hash classes, largest vertices first
+  if ((n = cnt(kClsH16K)) > 0) CVB_TRY((launch_hash<1024, 4, 2, 16384, 1>(e, e->aux[0], p, lst(kClsH16K), n, 1)));
+  if ((n = cnt(kClsH8K)) > 0) CVB_TRY((launch_hash<512, 4, 2, 8192, 1>(e, e->aux[0], p, lst(kClsH8K), n, 2)));
+  if ((n = cnt(kClsH4K)) > 0) CVB_TRY((launch_hash<256, 4, 2, 4096, 1>(e, e->aux[0], p, lst(kClsH4K), n, 4)));
+  if ((n = cnt(kClsH2K)) > 0) CVB_TRY((launch_hash<128, 4, 2, 2048, 1>(e, e->aux[0], p, lst(kClsH2K), n, 8)));
+  // stream 1: giants
+  if ((n = cnt(kClsGiant)) > 0) {
+    GiantTables gt;
+    gt.chunk_start = e->giant_layout.p;
+    gt.table_start = e->giant_layout.p + (n + 1);
+    gt.keys = e->gkeys.p;
+    gt.wts = e->gwts.p;
+    gt.ays = e->gays.p;
+    gt.gmeta = e->gmeta.p;
+    gt.piece_gain = e->gpiece_gain.p;
+    gt.piece_key = e->gpiece_key.p;
+    const int64_t pieces = e->giant_slots / kGiantPiece;
+    int64_t g1 = e->giant_chunks < 4LL * e->num_sms ? e->giant_chunks : 4LL * e->num_sms;
+    k_sweep_u32_giant_insert<<<static_cast<int>(g1), 512, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt,
+                                                                         e->giant_chunks);
+    int64_t g2 = pieces < 4LL * e->num_sms ? pieces : 4LL * e->num_sms;
+    k_sweep_u32_giant_eval<<<static_cast<int>(g2), 512, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt, pieces);
+    k_sweep_u32_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n,
+                                                                                         gt);
+    e->launches += 3;
+  }
+  // stream 2: warp-level hash classes
+  if ((n = cnt(kClsH1K)) > 0) CVB_TRY((launch_hash<64, 4, 2, 1024, 1>(e, e->aux[2], p, lst(kClsH1K), n, 16)));
+  if ((n = cnt(kClsH512)) > 0) CVB_TRY((launch_hash<32, 4, 2, 512, 8>(e, e->aux[2], p, lst(kClsH512), n, 4)));
+  if ((n = cnt(kClsH256)) > 0) CVB_TRY((launch_hash<32, 4, 1, 256, 8>(e, e->aux[2], p, lst(kClsH256), n, 8)));
+  if ((n = cnt(kClsH128)) > 0) CVB_TRY((launch_hash<32, 2, 1, 128, 8>(e, e->aux[2], p, lst(kClsH128), n, 8)));
+  // stream 3: the small classes
+  if ((n = cnt(kClsG32)) > 0) {
+    k_sweep_u32_group<32><<<static_cast<int>((n * 32 + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG32), (int)n);
+    e->launches++;
+  }
+  if ((n = cnt(kClsG16)) > 0) {
+    k_sweep_u32_group<16><<<static_cast<int>((n * 16 + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG16), (int)n);
+    e->launches++;
+  }
+  if ((n = cnt(kClsG8)) > 0) {
+    k_sweep_u32_group<8><<<static_cast<int>((n * 8 + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG8), (int)n);
+    e->launches++;
+  }
+  if ((n = cnt(kClsG4)) > 0) {
+    k_sweep_u32_t4<<<static_cast<int>((n + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG4), (int)n);
+    e->launches++;
+  }
+  for (int i = 0; i < cvb_engine::kAux; ++i) {
+    CVB_CUDA(cudaEventRecord(e->ev_join[i], e->aux[i]));
+    CVB_CUDA(cudaStreamWaitEvent(st, e->ev_join[i], 0));
   }
   CVB_CUDA(cudaGetLastError());
   return CVB_OK;
@@ -301,13 +412,38 @@ int finish_graph(cvb_engine *e, const void *d_aos, const int64_t *d_tails64, con
   e->local_weight = lw;
   // global-memory tables for the giant class
   const int64_t ngiant = e->class_start[kClsGiant + 1] - e->class_start[kClsGiant];
-  if (ngiant > 0) {
+  if (ngiant > 0 && e->mode == CVB_WEIGHTS_F64) {
     int lg = 14;
     while ((int64_t(1) << lg) < 2 * e->max_degree) ++lg;
     e->giant_log2cap = lg;
     e->giant_stride = ((sizeof(vid_t) + wbytes) << lg);
     e->giant_blocks = static_cast<int>(ngiant < 2 * e->num_sms ? ngiant : 2 * e->num_sms);
     CVB_TRY(e->giant.ensure(e->giant_stride * e->giant_blocks));
+  }
+  if (e->mode == CVB_WEIGHTS_U32) {
+    CVB_TRY(e->packed.ensure(e->nvg + 1));
+    if (ngiant > 0) {
+      CVB_TRY(e->giant_layout.ensure(2 * (ngiant + 1)));
+      k_giant_layout<<<1, 32, 0, st>>>(e->offsets.p, e->list.p + e->class_start[kClsGiant], (int)ngiant,
+                                       e->giant_layout.p, e->giant_layout.p + (ngiant + 1));
+      e->launches++;
+      int64_t tot[2];
+      CVB_CUDA(cudaMemcpyAsync(&tot[0], e->giant_layout.p + ngiant, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CVB_CUDA(cudaMemcpyAsync(&tot[1], e->giant_layout.p + (ngiant + 1) + ngiant, sizeof(int64_t),
+                               cudaMemcpyDeviceToHost, st));
+      CVB_CUDA(cudaStreamSynchronize(st));
+      e->giant_chunks = tot[0];
+      e->giant_slots = tot[1];
+      CVB_TRY(e->gkeys.ensure(e->giant_slots));
+      CVB_TRY(e->gwts.ensure(e->giant_slots));
+      CVB_TRY(e->gays.ensure(e->giant_slots));
+      CVB_TRY(e->gmeta.ensure(3 * ngiant + 4));
+      CVB_TRY(e->gpiece_gain.ensure(e->giant_slots / kGiantPiece + 1));
+      CVB_TRY(e->gpiece_key.ensure(e->giant_slots / kGiantPiece + 1));
+      CVB_CUDA(cudaMemsetAsync(e->gkeys.p, 0xFF, e->giant_slots * sizeof(uint32_t), st));
+      CVB_CUDA(cudaMemsetAsync(e->gwts.p, 0, e->giant_slots * sizeof(uint32_t), st));
+      CVB_CUDA(cudaMemsetAsync(e->gmeta.p, 0, (3 * ngiant + 4) * sizeof(uint32_t), st));
+    }
   }
   e->graph_ready = true;
   e->phase_ready = false;
@@ -367,10 +503,19 @@ cvb_engine *cvb_create(void *stream) {
     }
     e->own_stream = true;
   }
-  if (cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) {
+  if (cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
     set_error("cvb_create: cudaEventCreate failed");
     delete e;
     return nullptr;
+  }
+  for (int i = 0; i < cvb_engine::kAux; ++i) {
+    if (cudaStreamCreateWithFlags(&e->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+      set_error("cvb_create: auxiliary stream/event creation failed");
+      delete e;
+      return nullptr;
+    }
   }
   return e;
 }
@@ -386,6 +531,13 @@ void cvb_destroy(cvb_engine *e) {
   e->d_class_start.release(); e->d_class_entries.release();
   e->partials.release(); e->d_sums.release(); e->ticket.release(); e->d_flags.release();
   e->h_sums.release(); e->staging.release(); e->staging2.release(); e->giant.release(); e->h_stage.release();
+  e->packed.release(); e->giant_layout.release(); e->gkeys.release(); e->gwts.release(); e->gays.release();
+  e->gmeta.release(); e->gpiece_key.release(); e->gpiece_gain.release();
+  for (int i = 0; i < cvb_engine::kAux; ++i) {
+    if (e->aux[i]) cudaStreamDestroy(e->aux[i]);
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->own_stream) cudaStreamDestroy(e->stream);
@@ -486,7 +638,7 @@ int cvb_sweep(cvb_engine *e) {
   CVB_CHECK(e && e->phase_ready, CVB_ERR_STATE, "cvb_sweep: call cvb_phase_begin first");
   CVB_CUDA(cudaEventRecord(e->ev0, e->stream));
   if (e->mode == CVB_WEIGHTS_U32)
-    CVB_TRY(launch_sweep<uint32_t>(e));
+    CVB_TRY(launch_sweep_u32(e));
   else
     CVB_TRY(launch_sweep<double>(e));
   CVB_CUDA(cudaEventRecord(e->ev1, e->stream));

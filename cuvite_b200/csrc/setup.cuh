@@ -312,16 +312,34 @@ __global__ void __launch_bounds__(kReduceBlock) k_apply_reduce(int64_t nv_global
     last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last) {  // block-uniform: the last block adds the partials in a fixed order
     __threadfence();
     double te = 0.0, ta = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) {
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kReduceBlock) {
       te += __ldcg(&partials[2 * b]);
       ta += __ldcg(&partials[2 * b + 1]);
     }
-    out[0] = te;
-    out[1] = ta;
-    *ticket = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      te += __shfl_xor_sync(0xffffffffu, te, o);
+      ta += __shfl_xor_sync(0xffffffffu, ta, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      sh_e[threadIdx.x >> 5] = te;
+      sh_a[threadIdx.x >> 5] = ta;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double fe = 0.0, fa = 0.0;
+      for (int w = 0; w < kReduceBlock / 32; ++w) {
+        fe += sh_e[w];
+        fa += sh_a[w];
+      }
+      out[0] = fe;
+      out[1] = fa;
+      *ticket = 0;
+    }
   }
 }
 

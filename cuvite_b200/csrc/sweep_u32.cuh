@@ -1,0 +1,659 @@
+// sweep_u32.cuh — the fast local-move sweep for CVB_WEIGHTS_U32 graphs (all
+// weights non-negative integers, total < 2^32: every sum below is exact, so the
+// result is independent of accumulation order and bit-identical to the
+// reference's double arithmetic, louvain.cpp:2185-2431).
+//
+// Design, from measurements on B200 (profiles/r01_microbench_b200.txt):
+//   * shared-memory atomics run at ~8.9 lane-ops/clk/SM, as fast as plain
+//     random LDS, while match.any on 32 distinct keys costs 64 clk per warp —
+//     so the per-community accumulation is an open-addressing hash in shared
+//     memory claimed with atomicCAS and accumulated with atomicAdd;
+//   * the binding resource is the random per-entry gather (~290 G sectors/s out
+//     of L2) — so labels are PACKED: one 8-byte entry per vertex holds the
+//     vertex's community, a "community is a singleton" bit and the community's
+//     degree, and a single gather per CSR entry brings everything the gain needs
+//     (no second gather into the community-info arrays, no size lookups);
+//   * cost after the insert phase is proportional to the number of DISTINCT
+//     neighbour communities (the lane that claimed a slot evaluates it), not to
+//     the table capacity.
+#pragma once
+
+#include <climits>
+
+#include "common.cuh"
+#include "sweep.cuh"
+
+namespace cvb {
+
+constexpr uint32_t kEmptyKeyU = 0xFFFFFFFFu;
+constexpr uint32_t kLabelMask = 0x7FFFFFFFu;
+constexpr uint32_t kSingletonBit = 0x80000000u;
+
+struct SweepU32Params {
+  const eid_t *__restrict__ offsets;    // [nv_local+1]
+  const vid_t *__restrict__ tails;      // [ne]
+  const uint32_t *__restrict__ weights; // [ne]
+  const uint2 *__restrict__ packed;     // [nv_global] {label | singleton<<31, degree of that community}
+  const double *__restrict__ vdeg;      // [nv_local]
+  double constant;
+  vid_t base;
+  vid_t *__restrict__ target;  // [nv_local]
+  double *__restrict__ cw;     // [nv_local]
+  double *__restrict__ ddeg;   // [nv_global]
+  int32_t *__restrict__ dsize; // [nv_global]
+};
+
+// packed[v] = {labels[v] | (csize[labels[v]] == 1) << 31, (uint32) cdeg[labels[v]]}
+__global__ void k_pack_labels(int64_t nv_global, const vid_t *__restrict__ labels, const double *__restrict__ cdeg,
+                              const int32_t *__restrict__ csize, uint2 *__restrict__ packed) {
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < nv_global;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const vid_t l = labels[v];
+    const uint32_t flag = (csize[l] == 1) ? kSingletonBit : 0u;
+    packed[v] = make_uint2(static_cast<uint32_t>(l) | flag, static_cast<uint32_t>(cdeg[l]));
+  }
+}
+
+__device__ __forceinline__ uint32_t hash_key(uint32_t key, int log2cap) {
+  return ((key & kLabelMask) * 2654435761u) >> (32 - log2cap);
+}
+
+// best-candidate bookkeeping: ids carry the singleton bit in bit 31
+__device__ __forceinline__ bool better_u(double g2, uint32_t id2, double g, uint32_t id) {
+  return (g2 > g) || (g2 == g && (id2 & kLabelMask) < (id & kLabelMask));
+}
+
+__device__ __forceinline__ void commit_vertex_u32(const SweepU32Params &p, vid_t v, uint32_t me_key, double best_gain,
+                                                  uint32_t best_key, double vd, double counter0) {
+  const vid_t cc = static_cast<vid_t>(me_key & kLabelMask);
+  vid_t best = (best_gain > 0.0) ? static_cast<vid_t>(best_key & kLabelMask) : cc;
+  // louvain.cpp:2240-2241: two singletons only ever merge towards the smaller id
+  if (best != cc && best > cc && (best_key & kSingletonBit) && (me_key & kSingletonBit)) best = cc;
+  p.target[v] = best;
+  p.cw[v] = counter0;
+  if (best != cc) {
+    atomicAdd(&p.ddeg[best], vd);
+    atomicAdd(&p.dsize[best], 1);
+    atomicAdd(&p.ddeg[cc], -vd);
+    atomicAdd(&p.dsize[cc], -1);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// deg 1..4: one thread per vertex, everything in registers.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sweep_u32_t4(SweepU32Params p, const vid_t *__restrict__ list, int n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const vid_t v = list[i];
+  const eid_t e0 = p.offsets[v];
+  const int deg = static_cast<int>(p.offsets[v + 1] - e0);
+  const vid_t self = v + p.base;
+  const uint2 me = p.packed[self];
+  const uint32_t cc = me.x & kLabelMask;
+  const double vd = p.vdeg[v];
+  uint32_t key[4], w[4], ay[4];
+  uint32_t selfloop = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    key[j] = kEmptyKeyU;
+    w[j] = 0;
+    ay[j] = 0;
+    if (j < deg) {
+      const vid_t t = p.tails[e0 + j];
+      w[j] = p.weights[e0 + j];
+      const uint2 pk = p.packed[t];
+      key[j] = pk.x;
+      ay[j] = pk.y;
+      if (t == self) selfloop += w[j];
+    }
+  }
+  // merge duplicates into the first occurrence
+#pragma unroll
+  for (int j = 1; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < j; ++k)
+      if (key[j] != kEmptyKeyU && key[j] == key[k]) {
+        w[k] += w[j];
+        key[j] = kEmptyKeyU;
+      }
+  uint32_t c0 = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (key[j] != kEmptyKeyU && (key[j] & kLabelMask) == cc) c0 = w[j];
+  const double counter0 = static_cast<double>(c0);
+  const double eix = counter0 - static_cast<double>(selfloop);
+  const double ax = static_cast<double>(me.y) - vd;
+  double g = -1.0;
+  uint32_t id = kLabelMask;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (key[j] != kEmptyKeyU && (key[j] & kLabelMask) != cc) {
+      const double g2 = modularity_gain(static_cast<double>(w[j]), eix, vd, static_cast<double>(ay[j]), ax, p.constant);
+      if (better_u(g2, key[j], g, id)) {
+        g = g2;
+        id = key[j];
+      }
+    }
+  commit_vertex_u32(p, v, me.x, g, id, vd, counter0);
+}
+
+// ---------------------------------------------------------------------------
+// deg 5..32: G lanes per vertex, one batch, duplicates merged with match.any.
+// ---------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256) k_sweep_u32_group(SweepU32Params p, const vid_t *__restrict__ list, int n) {
+  const unsigned lane = threadIdx.x & 31u;
+  const int lig = static_cast<int>(lane) & (G - 1);
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~static_cast<unsigned>(G - 1)));
+  const int64_t gid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / G;
+  if (gid >= n) return;
+  const vid_t v = list[gid];
+  const eid_t e0 = p.offsets[v];
+  const int deg = static_cast<int>(p.offsets[v + 1] - e0);
+  const vid_t self = v + p.base;
+  const uint2 me = p.packed[self];
+  const uint32_t cc = me.x & kLabelMask;
+  const bool valid = lig < deg;
+  vid_t tail = -1;
+  uint32_t w = 0, ay = 0;
+  uint32_t key = 0xFFFFFF00u + lig;  // distinct idle keys (never a real label)
+  if (valid) {
+    tail = p.tails[e0 + lig];
+    w = p.weights[e0 + lig];
+    const uint2 pk = p.packed[tail];
+    key = pk.x;
+    ay = pk.y;
+  }
+  const unsigned m = __match_any_sync(gmask, key);
+  const bool leader = valid && (static_cast<unsigned>(__ffs(m) - 1) == lane);
+  const uint32_t s = group_sum_ordered<uint32_t>(gmask, m, w, 0u, lane);
+  const unsigned ccb = __ballot_sync(gmask, leader && (key & kLabelMask) == cc);
+  const uint32_t c0 = __shfl_sync(gmask, s, ccb ? (__ffs(ccb) - 1) : static_cast<int>(lane));
+  const double counter0 = ccb ? static_cast<double>(c0) : 0.0;
+  unsigned slb = __ballot_sync(gmask, valid && tail == self);
+  double selfloop = 0.0;
+  while (slb) {
+    selfloop += static_cast<double>(__shfl_sync(gmask, w, __ffs(slb) - 1));
+    slb &= slb - 1u;
+  }
+  const double vd = p.vdeg[v];
+  const double eix = counter0 - selfloop;
+  const double ax = static_cast<double>(me.y) - vd;
+  double g = -1.0;
+  uint32_t id = kLabelMask;
+  if (leader && (key & kLabelMask) != cc) {
+    g = modularity_gain(static_cast<double>(s), eix, vd, static_cast<double>(ay), ax, p.constant);
+    id = key;
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const double g2 = __shfl_xor_sync(gmask, g, o);
+    const uint32_t id2 = __shfl_xor_sync(gmask, id, o);
+    if (better_u(g2, id2, g, id)) {
+      g = g2;
+      id = id2;
+    }
+  }
+  if (lig == 0) commit_vertex_u32(p, v, me.x, g, id, vd, counter0);
+}
+
+// ---------------------------------------------------------------------------
+// deg 33..8192: TPV threads per vertex, K CSR entries per thread, hash table
+// {keys, wts} in shared memory.
+//   TPV == 32 : VPB warps per block, each warp owns a vertex and a table
+//   TPV  > 32 : the whole block owns one vertex
+// Persistent blocks stride over the class list.  A lane that CLAIMS a slot for
+// a new key remembers the slot in a register and is the one that evaluates that
+// community's gain after the last insert, then frees the slot — so there is no
+// per-table list and no table scan, and the cost after the insert phase is
+// proportional to the number of distinct neighbour communities.
+// Per table: keys[CAP] wts[CAP] ays[CAP] (uint32), meta[4] = {-, selfloop, counter0, -}.
+// ---------------------------------------------------------------------------
+template <int CAP>
+__host__ __device__ constexpr size_t hash_table_bytes() {
+  return static_cast<size_t>(CAP) * 12 + 16;
+}
+
+template <int TPV>
+__device__ __forceinline__ void tile_sync() {
+  if (TPV == 32)
+    __syncwarp();
+  else
+    __syncthreads();
+}
+
+// Warp argmax under the (gain desc, id asc) order, gains > 0 only, with three
+// REDUX operations: positive doubles order like their bit patterns.
+// Returns the winning key (singleton bit included) or kLabelMask when no lane
+// holds a positive gain; *gain_out gets the winning gain (or -1).
+__device__ __forceinline__ uint32_t warp_argmax(double g, uint32_t key, double *gain_out) {
+  const unsigned long long gb = (g > 0.0) ? static_cast<unsigned long long>(__double_as_longlong(g)) : 0ull;
+  const uint32_t hi = static_cast<uint32_t>(gb >> 32), lo = static_cast<uint32_t>(gb);
+  const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
+  const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  const bool top = gb != 0ull && hi == mhi && lo == mlo;
+  const uint32_t mid = __reduce_min_sync(0xffffffffu, top ? (key & kLabelMask) : 0xFFFFFFFFu);
+  const unsigned who = __ballot_sync(0xffffffffu, top && (key & kLabelMask) == mid);
+  if (who == 0u) {
+    *gain_out = -1.0;
+    return kLabelMask;
+  }
+  *gain_out = __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(mhi) << 32) | mlo));
+  return __shfl_sync(0xffffffffu, key, __ffs(who) - 1);
+}
+
+// Shared-memory accesses by 32-bit shared address (one address register +
+// immediate offset in SASS instead of re-deriving generic pointers).
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  // opaque move: keeps the address in one register instead of letting ptxas
+  // re-derive the shared window base (S2UR/UMOV/ULEA) at every access
+  asm volatile("mov.u32 %0, %0;" : "+r"(a));
+  return a;
+}
+__device__ __forceinline__ uint32_t atoms_cas(uint32_t addr, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ void reds_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// Second hash for double hashing: an odd step, so every slot of the
+// power-of-two table is reachable.
+__device__ __forceinline__ uint32_t hash_step(uint32_t key, int log2cap) {
+  return ((((key & kLabelMask) * 0x85EBCA6Bu) >> (32 - log2cap)) | 1u);
+}
+
+// Insert KC entries per lane into the open-addressing table.  kaddr is the
+// shared address of keys[]; wts[] and ays[] follow at +capb and +2*capb bytes.
+// All KC first-probe claims are issued back to back (independent shared-memory
+// atomics in flight); a collided entry then walks its own short probe loop
+// (double hashing).  Bit k of the return value is set when this lane claimed a
+// fresh slot for entry k; slb[k] is the entry's final slot as a BYTE offset.
+template <int KC>
+__device__ __forceinline__ uint32_t table_insert_chunk(uint32_t kaddr, uint32_t capb, const uint32_t (&key)[KC],
+                                                       const uint32_t (&ay)[KC], const uint32_t (&w)[KC],
+                                                       uint32_t active, int log2cap, uint32_t maskb,
+                                                       uint32_t (&slb)[KC]) {
+  uint32_t old[KC];
+  uint32_t fresh = 0u;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    slb[k] = hash_key(key[k], log2cap) << 2;
+    old[k] = kEmptyKeyU;
+    if (active & (1u << k)) old[k] = atoms_cas(kaddr + slb[k], kEmptyKeyU, key[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < KC; ++k)
+    if (active & (1u << k)) {
+      if (old[k] == kEmptyKeyU) {
+        fresh |= 1u << k;
+      } else if (old[k] != key[k]) {
+        const uint32_t step = hash_step(key[k], log2cap) << 2;
+        while (true) {
+          slb[k] = (slb[k] + step) & maskb;
+          const uint32_t o = atoms_cas(kaddr + slb[k], kEmptyKeyU, key[k]);
+          if (o == kEmptyKeyU) {
+            fresh |= 1u << k;
+            break;
+          }
+          if (o == key[k]) break;
+        }
+      }
+    }
+#pragma unroll
+  for (int k = 0; k < KC; ++k)
+    if (active & (1u << k)) {
+      reds_add(kaddr + capb + slb[k], w[k]);
+      if (fresh & (1u << k)) sts_u32(kaddr + 2u * capb + slb[k], ay[k]);
+    }
+  return fresh;
+}
+
+// K = KC * NCH entries per thread, processed in NCH chunks of KC.
+template <int TPV, int KC, int NCH, int CAP, int VPB>
+__global__ void __launch_bounds__(TPV *VPB) k_sweep_u32_hash(SweepU32Params p, const vid_t *__restrict__ list, int n) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  __shared__ double red_g[32];
+  __shared__ uint32_t red_id[32];
+  constexpr int kWarpsPerVertex = TPV / 32;
+  constexpr uint32_t capb = CAP * 4u;
+  constexpr int kWords = CAP * 3 + 4;
+  const unsigned lane = threadIdx.x & 31u;
+  const int tid = (TPV == 32) ? static_cast<int>(lane) : static_cast<int>(threadIdx.x);
+  const int vslot = (TPV == 32) ? static_cast<int>(threadIdx.x >> 5) : 0;
+  const int wiv = (TPV == 32) ? 0 : static_cast<int>(threadIdx.x >> 5);  // warp in vertex
+  uint32_t *keys = smem_u32 + kWords * vslot;
+  uint32_t *wts = keys + CAP;
+  uint32_t *meta = keys + 3 * CAP;
+  const uint32_t kaddr = smem_addr(keys);
+  for (int s = tid; s < CAP; s += TPV) {
+    keys[s] = kEmptyKeyU;
+    wts[s] = 0u;
+  }
+  if (tid < 4) meta[tid] = 0u;
+  tile_sync<TPV>();
+
+  for (int64_t item = static_cast<int64_t>(blockIdx.x) * VPB + vslot; item < n;
+       item += static_cast<int64_t>(gridDim.x) * VPB) {
+    const vid_t v = list[item];
+    const eid_t e0 = p.offsets[v], e1 = p.offsets[v + 1];
+    const int deg = static_cast<int>(e1 - e0);
+    const vid_t self = v + p.base;
+    const uint2 me = p.packed[self];
+    const uint32_t cc = me.x & kLabelMask;
+    const double vd = p.vdeg[v];
+    int log2cap = 32 - __clz(2 * deg - 1);  // ceil(log2(2*deg)): load factor <= 0.5
+    log2cap = log2cap < 6 ? 6 : (log2cap > 31 - __clz(CAP) ? 31 - __clz(CAP) : log2cap);
+    const uint32_t maskb = ((1u << log2cap) - 1u) << 2;
+
+    uint16_t claimed[NCH][KC];  // byte offsets / 4 of the slots this lane claimed
+    uint32_t freshmask = 0u, ownsum = 0u;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if (c * KC * TPV < deg) {  // tile-uniform
+        uint32_t key[KC], ay[KC], w[KC], slb[KC];
+        vid_t tail[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const eid_t e = e0 + tid + static_cast<eid_t>(c * KC + k) * TPV;
+          tail[k] = -1;
+          w[k] = 0u;
+          if (e < e1) {
+            tail[k] = p.tails[e];
+            w[k] = p.weights[e];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          key[k] = kEmptyKeyU;
+          ay[k] = 0u;
+          if (tail[k] >= 0) {
+            const uint2 pk = p.packed[tail[k]];
+            key[k] = pk.x;
+            ay[k] = pk.y;
+          }
+        }
+        uint32_t active = 0u;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const bool valid = tail[k] >= 0;
+          if (valid && tail[k] == self) atomicAdd(&meta[1], w[k]);
+          const bool own = valid && (key[k] & kLabelMask) == cc;
+          if (own) ownsum += w[k];
+          if (valid && !own) active |= 1u << k;
+        }
+        const uint32_t fresh = table_insert_chunk<KC>(kaddr, capb, key, ay, w, active, log2cap, maskb, slb);
+        freshmask |= fresh << (c * KC);
+#pragma unroll
+        for (int k = 0; k < KC; ++k) claimed[c][k] = static_cast<uint16_t>(slb[k] >> 2);
+      }
+    }
+    {  // own-community weight: one REDUX + one atomic per warp
+      const uint32_t s = __reduce_add_sync(0xffffffffu, ownsum);
+      if (lane == 0 && s) atomicAdd(&meta[2], s);
+    }
+    tile_sync<TPV>();
+
+    // ---- evaluate: the claimer of each key reads its total and frees the slot ----
+    const double counter0 = static_cast<double>(meta[2]);
+    const double eix = counter0 - static_cast<double>(meta[1]);
+    const double ax = static_cast<double>(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int k = 0; k < KC; ++k)
+        if (freshmask & (1u << (c * KC + k))) {
+          const uint32_t a = kaddr + (static_cast<uint32_t>(claimed[c][k]) << 2);
+          const uint32_t kk = lds_u32(a);
+          const uint32_t tot = lds_u32(a + capb);
+          const uint32_t ayv = lds_u32(a + 2u * capb);
+          sts_u32(a, kEmptyKeyU);
+          sts_u32(a + capb, 0u);
+          const double g2 = modularity_gain(static_cast<double>(tot), eix, vd, static_cast<double>(ayv), ax, p.constant);
+          if (better_u(g2, kk, g, id)) {
+            g = g2;
+            id = kk;
+          }
+        }
+    double wg;
+    uint32_t wid = warp_argmax(g, id, &wg);
+    if (TPV == 32) {
+      if (lane == 0) {
+        commit_vertex_u32(p, v, me.x, wg, wid, vd, counter0);
+        meta[1] = 0u;
+        meta[2] = 0u;
+      }
+      __syncwarp();
+    } else {
+      if (lane == 0) {
+        red_g[wiv] = wg;
+        red_id[wiv] = wid;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int i = 1; i < kWarpsPerVertex; ++i)
+          if (better_u(red_g[i], red_id[i], wg, wid)) {
+            wg = red_g[i];
+            wid = red_id[i];
+          }
+        commit_vertex_u32(p, v, me.x, wg, wid, vd, counter0);
+        meta[1] = 0u;
+        meta[2] = 0u;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// deg > 8192: tables in global memory, three kernels.
+//   k_sweep_u32_giant_insert : blocks take 4096-entry chunks of giant
+//       adjacencies (chunk -> vertex by binary search in chunk_start) and
+//       insert into that vertex's table with L2 atomics;
+//   k_sweep_u32_giant_eval   : blocks take 8192-slot pieces of the tables,
+//       evaluate the gains of the keys found there, free the slots and leave one
+//       (gain, key) candidate per piece;
+//   k_sweep_u32_giant_final  : one warp per giant vertex reduces its pieces'
+//       candidates and commits.
+// gmeta[3*i + {1,2}] = {selfloop, counter0} of giant i.
+// ---------------------------------------------------------------------------
+constexpr int kGiantChunk = 4096;
+constexpr int kGiantPiece = 8192;  // table capacities are multiples of this
+
+struct GiantTables {
+  const int64_t *__restrict__ chunk_start;  // [ngiant+1] prefix of chunks per vertex
+  const int64_t *__restrict__ table_start;  // [ngiant+1] prefix of table slots per vertex
+  uint32_t *__restrict__ keys;
+  uint32_t *__restrict__ wts;
+  uint32_t *__restrict__ ays;
+  uint32_t *__restrict__ gmeta;
+  double *__restrict__ piece_gain;   // [total_slots / kGiantPiece]
+  uint32_t *__restrict__ piece_key;  // [total_slots / kGiantPiece]
+};
+
+__global__ void k_giant_layout(const eid_t *__restrict__ offsets, const vid_t *__restrict__ list, int n,
+                               int64_t *__restrict__ chunk_start, int64_t *__restrict__ table_start) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int64_t c = 0, s = 0;
+  for (int i = 0; i < n; ++i) {
+    chunk_start[i] = c;
+    table_start[i] = s;
+    const int64_t deg = offsets[list[i] + 1] - offsets[list[i]];
+    c += (deg + kGiantChunk - 1) / kGiantChunk;
+    int64_t cap = 16384;
+    while (cap < 2 * deg) cap <<= 1;
+    s += cap;
+  }
+  chunk_start[n] = c;
+  table_start[n] = s;
+}
+
+__device__ __forceinline__ int giant_owner(const int64_t *__restrict__ start, int n, int64_t x) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (start[mid] <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(512) k_sweep_u32_giant_insert(SweepU32Params p, const vid_t *__restrict__ list, int n,
+                                                               GiantTables gt, int64_t total_chunks) {
+  constexpr int KG = kGiantChunk / 512;  // entries per thread per chunk
+  const unsigned lane = threadIdx.x & 31u;
+  for (int64_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    const int gi = giant_owner(gt.chunk_start, n, chunk);
+    const vid_t v = list[gi];
+    const eid_t e0 = p.offsets[v], e1 = p.offsets[v + 1];
+    const eid_t c0e = e0 + (chunk - gt.chunk_start[gi]) * kGiantChunk;
+    const eid_t c1e = (c0e + kGiantChunk < e1) ? c0e + kGiantChunk : e1;
+    const vid_t self = v + p.base;
+    const uint32_t cc = p.packed[self].x & kLabelMask;
+    const int64_t tbase = gt.table_start[gi];
+    const int64_t cap = gt.table_start[gi + 1] - tbase;
+    const int log2cap = 63 - __clzll(cap);
+    const uint32_t mask = static_cast<uint32_t>(cap - 1);
+    uint32_t *keys = gt.keys + tbase, *wts = gt.wts + tbase, *ays = gt.ays + tbase;
+    uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
+    vid_t tail[KG];
+    uint32_t w[KG];
+    uint2 pk[KG];
+#pragma unroll
+    for (int k = 0; k < KG; ++k) {
+      const eid_t e = c0e + threadIdx.x + static_cast<eid_t>(k) * 512;
+      tail[k] = -1;
+      w[k] = 0u;
+      if (e < c1e) {
+        tail[k] = p.tails[e];
+        w[k] = p.weights[e];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KG; ++k) {
+      pk[k] = make_uint2(kEmptyKeyU, 0u);
+      if (tail[k] >= 0) pk[k] = p.packed[tail[k]];
+    }
+    uint32_t ownsum = 0u;
+#pragma unroll
+    for (int k = 0; k < KG; ++k) {
+      const bool valid = tail[k] >= 0;
+      if (valid && tail[k] == self) atomicAdd(&meta[1], w[k]);
+      const bool own = valid && (pk[k].x & kLabelMask) == cc;
+      if (own) ownsum += w[k];
+      if (valid && !own) {
+        uint32_t slot = hash_key(pk[k].x, log2cap);
+        while (true) {
+          const uint32_t old = atomicCAS(&keys[slot], kEmptyKeyU, pk[k].x);
+          if (old == kEmptyKeyU) {
+            ays[slot] = pk[k].y;
+            break;
+          }
+          if (old == pk[k].x) break;
+          slot = (slot + 1u) & mask;
+        }
+        atomicAdd(&wts[slot], w[k]);
+      }
+    }
+    const uint32_t s = __reduce_add_sync(0xffffffffu, ownsum);
+    if (lane == 0 && s) atomicAdd(&meta[2], s);
+  }
+}
+
+__global__ void __launch_bounds__(512) k_sweep_u32_giant_eval(SweepU32Params p, const vid_t *__restrict__ list, int n,
+                                                             GiantTables gt, int64_t total_pieces) {
+  __shared__ double red_g[16];
+  __shared__ uint32_t red_id[16];
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = threadIdx.x >> 5;
+  for (int64_t piece = blockIdx.x; piece < total_pieces; piece += gridDim.x) {
+    const int64_t s0 = piece * kGiantPiece;
+    const int gi = giant_owner(gt.table_start, n, s0);
+    const vid_t v = list[gi];
+    const uint2 me = p.packed[v + p.base];
+    const double vd = p.vdeg[v];
+    const uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
+    const double counter0 = static_cast<double>(__ldcg(&meta[2]));
+    const double eix = counter0 - static_cast<double>(__ldcg(&meta[1]));
+    const double ax = static_cast<double>(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+    uint32_t k[kGiantPiece / 512];
+#pragma unroll
+    for (int j = 0; j < kGiantPiece / 512; ++j) k[j] = __ldcg(&gt.keys[s0 + threadIdx.x + j * 512]);
+#pragma unroll
+    for (int j = 0; j < kGiantPiece / 512; ++j) {
+      if (k[j] != kEmptyKeyU) {
+        const int64_t s = s0 + threadIdx.x + j * 512;
+        const double g2 = modularity_gain(static_cast<double>(__ldcg(&gt.wts[s])), eix, vd,
+                                          static_cast<double>(__ldcg(&gt.ays[s])), ax, p.constant);
+        gt.keys[s] = kEmptyKeyU;
+        gt.wts[s] = 0u;
+        if (better_u(g2, k[j], g, id)) {
+          g = g2;
+          id = k[j];
+        }
+      }
+    }
+    double wg;
+    uint32_t wid = warp_argmax(g, id, &wg);
+    if (lane == 0) {
+      red_g[wib] = wg;
+      red_id[wib] = wid;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < 16; ++i)
+        if (better_u(red_g[i], red_id[i], wg, wid)) {
+          wg = red_g[i];
+          wid = red_id[i];
+        }
+      gt.piece_gain[piece] = wg;
+      gt.piece_key[piece] = wid;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(128) k_sweep_u32_giant_final(SweepU32Params p, const vid_t *__restrict__ list, int n,
+                                                              GiantTables gt) {
+  const int gi = static_cast<int>((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+  const unsigned lane = threadIdx.x & 31u;
+  if (gi >= n) return;
+  const vid_t v = list[gi];
+  const uint2 me = p.packed[v + p.base];
+  const int64_t p0 = gt.table_start[gi] / kGiantPiece, p1 = gt.table_start[gi + 1] / kGiantPiece;
+  double g = -1.0;
+  uint32_t id = kLabelMask;
+  for (int64_t q = p0 + lane; q < p1; q += 32) {
+    const double g2 = gt.piece_gain[q];
+    const uint32_t k2 = gt.piece_key[q];
+    if (better_u(g2, k2, g, id)) {
+      g = g2;
+      id = k2;
+    }
+  }
+  double wg;
+  const uint32_t wid = warp_argmax(g, id, &wg);
+  if (lane == 0) {
+    uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
+    commit_vertex_u32(p, v, me.x, wg, wid, p.vdeg[v], static_cast<double>(meta[2]));
+    meta[1] = 0u;
+    meta[2] = 0u;
+  }
+}
+
+}  // namespace cvb

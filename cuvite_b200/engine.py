@@ -27,7 +27,7 @@ WEIGHTS_U32, WEIGHTS_F64 = 1, 2
 LABELS_PAST, LABELS_CURR, LABELS_TARGET = 0, 1, 2
 BUF = dict(labels_global=0, labels_curr=1, labels_target=2, labels_past=3, cdeg=4, csize=5, ddeg=6, dsize=7,
            vdeg=8, cw=9, offsets=10, tails=11, weights=12)
-CLASS_NAMES = ["deg0", "g4", "g8", "g16", "g32", "warp256", "warp1k", "block4k", "block16k", "giant"]
+CLASS_NAMES = ["deg0", "d4", "d8", "d16", "d32", "d64", "d128", "d256", "d512", "d1k", "d2k", "d4k", "d8k", "giant"]
 
 
 def _ptr(a):
