@@ -1,0 +1,123 @@
+// coarsen.cuh — next-level graph construction on the device: the one-rank path
+// of distbuildNextLevelGraph (rebuild.cpp:430-454).
+//   distReNumber      (rebuild.cpp:72-85)   communities are numbered in order of
+//                     first appearance of cvect[i], i ascending;
+//   fill_newEdgesMap  (rebuild.cpp:244-279) entry (i -> t, w) becomes
+//                     (newid[cvect[i]] -> newid[cvect[t]], w), parallel entries
+//                     summed in the order met (i ascending, j ascending);
+//   send_newEdges     (rebuild.cpp:405-427) CSR emitted with each adjacency
+//                     sorted by tail (std::map order).
+// Sorting / scanning uses CUB (library code, not on the sweep hot path); a
+// stable radix sort keeps the reference's summation order, and in
+// CVB_WEIGHTS_F64 mode each merged entry is summed sequentially in that order,
+// so the new weights are bit-identical to the reference's.
+#pragma once
+
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace cvb {
+
+__global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    p[i] = v;
+}
+
+// first[c] = smallest vertex index whose community is c
+__global__ void k_first_appearance(const vid_t *__restrict__ cvect, int64_t nv, int32_t *__restrict__ first) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    atomicMin(&first[cvect[i]], static_cast<int32_t>(i));
+}
+
+__global__ void k_flag_first(const vid_t *__restrict__ cvect, const int32_t *__restrict__ first, int64_t nv,
+                             int32_t *__restrict__ flag) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    flag[i] = (first[cvect[i]] == static_cast<int32_t>(i)) ? 1 : 0;
+}
+
+// vnew[i] = new id of vertex i's community = rank[first[cvect[i]]]
+__global__ void k_vertex_newid(const vid_t *__restrict__ cvect, const int32_t *__restrict__ first,
+                               const int32_t *__restrict__ rank, int64_t nv, int32_t *__restrict__ vnew) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    vnew[i] = rank[first[cvect[i]]];
+}
+
+// compose[p] = vnew[compose[p]]  (main.cpp:401-404 with rebuild's numbering)
+__global__ void k_compose(int32_t *__restrict__ compose, const int32_t *__restrict__ vnew, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    compose[i] = vnew[compose[i]];
+}
+
+__global__ void k_iota_i32(int32_t *p, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    p[i] = static_cast<int32_t>(i);
+}
+
+// One warp per row: key[e] = (vnew[row] << 32) | vnew[tail[e]]
+__global__ void k_edge_keys(const eid_t *__restrict__ offsets, const vid_t *__restrict__ tails,
+                            const int32_t *__restrict__ vnew, int64_t nv, uint64_t *__restrict__ keys) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  if (row >= nv) return;
+  const uint64_t hi = static_cast<uint64_t>(static_cast<uint32_t>(vnew[row])) << 32;
+  for (eid_t e = offsets[row] + lane; e < offsets[row + 1]; e += 32)
+    keys[e] = hi | static_cast<uint32_t>(vnew[tails[e]]);
+}
+
+// head[e] = 1 where a new (src, dst) pair starts in the sorted key array
+__global__ void k_heads(const uint64_t *__restrict__ keys, int64_t ne, int32_t *__restrict__ head) {
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < ne;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    head[e] = (e == 0 || keys[e] != keys[e - 1]) ? 1 : 0;
+}
+
+// seg[e] = inclusive-scan(head)[e] - 1 is the merged entry of sorted entry e.
+// Emits tails, per-row counts and the start of each merged entry.
+__global__ void k_emit_entries(const uint64_t *__restrict__ keys, const int32_t *__restrict__ head,
+                               const int32_t *__restrict__ seg_incl, int64_t ne, vid_t *__restrict__ ntails,
+                               int64_t *__restrict__ seg_start, unsigned long long *__restrict__ row_count) {
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < ne;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    if (head[e]) {
+      const int32_t s = seg_incl[e] - 1;
+      ntails[s] = static_cast<vid_t>(keys[e] & 0xFFFFFFFFull);
+      seg_start[s] = e;
+      atomicAdd(&row_count[keys[e] >> 32], 1ull);
+    }
+}
+
+// Weight of merged entry s = sum of the sorted weights in [seg_start[s], seg_start[s+1])
+// added sequentially (the reference's order).  One thread per merged entry for
+// short runs; long runs (heavy self-loops of big communities) use a warp when
+// the order is irrelevant (uint32) — see k_sum_segments_u32.
+__global__ void k_sum_segments_f64(const double *__restrict__ w_sorted, const int64_t *__restrict__ seg_start,
+                                   int64_t nseg, int64_t ne, double *__restrict__ out) {
+  for (int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; s < nseg;
+       s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t a = seg_start[s], b = (s + 1 < nseg) ? seg_start[s + 1] : ne;
+    double acc = 0.0;
+    for (int64_t e = a; e < b; ++e) acc += w_sorted[e];
+    out[s] = acc;
+  }
+}
+
+__global__ void k_sum_segments_u32(const uint32_t *__restrict__ w_sorted, const int64_t *__restrict__ seg_start,
+                                   int64_t nseg, int64_t ne, uint32_t *__restrict__ out) {
+  const int64_t s = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  if (s >= nseg) return;
+  const int64_t a = seg_start[s], b = (s + 1 < nseg) ? seg_start[s + 1] : ne;
+  uint32_t acc = 0u;
+  for (int64_t e = a + lane; e < b; e += 32) acc += w_sorted[e];
+  acc = __reduce_add_sync(0xffffffffu, acc);
+  if (lane == 0) out[s] = acc;
+}
+
+}  // namespace cvb

@@ -8,6 +8,7 @@
 #include "setup.cuh"
 #include "sweep.cuh"
 #include "sweep_u32.cuh"
+#include "coarsen.cuh"
 
 namespace cvb {
 
@@ -313,54 +314,18 @@ int launch_sweep_u32(cvb_engine *e) {
   return CVB_OK;
 }
 
-// Everything after the CSR is on the device in boundary layout: pick the
-// weight mode, narrow, compute vertex degrees, build the degree-class lists.
-int finish_graph(cvb_engine *e, const void *d_aos, const int64_t *d_tails64, const double *d_w64) {
-  const int64_t ne = e->ne, nvl = e->nvl;
+// The graph is on the device in device layout (offsets / int32 tails / weights
+// in e->mode): allocate the per-vertex state, compute vertex degrees, build the
+// degree-class lists and the giant-class tables.
+int post_graph(cvb_engine *e) {
+  const int64_t nvl = e->nvl;
   cudaStream_t st = e->stream;
-  CVB_TRY(e->d_flags.ensure(4));
+  const size_t wbytes = e->mode == CVB_WEIGHTS_U32 ? 4 : 8;
   CVB_TRY(e->d_sums.ensure(4));
   CVB_TRY(e->h_sums.ensure(64));
   CVB_TRY(e->ticket.ensure(4));
   CVB_TRY(e->partials.ensure(2 * 148 * 16 + 16));
-  CVB_CUDA(cudaMemsetAsync(e->d_flags.p, 0, 4 * sizeof(int), st));
-  CVB_CUDA(cudaMemsetAsync(e->d_sums.p, 0, 4 * sizeof(double), st));
   CVB_CUDA(cudaMemsetAsync(e->ticket.p, 0, 4 * sizeof(unsigned int), st));
-  if (ne > 0) {
-    if (d_aos)
-      k_weight_stats<true><<<grid_for(ne, 256), 256, 0, st>>>(d_aos, ne, e->d_flags.p, e->d_sums.p);
-    else
-      k_weight_stats<false><<<grid_for(ne, 256), 256, 0, st>>>(d_w64, ne, e->d_flags.p, e->d_sums.p);
-    e->launches++;
-  }
-  int flags = 0;
-  double wsum = 0.0;
-  CVB_CUDA(cudaMemcpyAsync(&flags, e->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CVB_CUDA(cudaMemcpyAsync(&wsum, e->d_sums.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-  CVB_CUDA(cudaStreamSynchronize(st));
-  e->mode = (flags == 0 && wsum < 4294967296.0) ? CVB_WEIGHTS_U32 : CVB_WEIGHTS_F64;
-  const size_t wbytes = e->mode == CVB_WEIGHTS_U32 ? 4 : 8;
-  CVB_TRY(e->tails.ensure(static_cast<size_t>(ne) + 1));
-  CVB_TRY(e->weights.ensure((static_cast<size_t>(ne) + 1) * wbytes));
-  if (ne > 0) {
-    const int g = grid_for(ne, 256);
-    if (e->mode == CVB_WEIGHTS_U32) {
-      if (d_aos)
-        k_convert_edges<true, uint32_t><<<g, 256, 0, st>>>(d_aos, nullptr, nullptr, ne, e->tails.p,
-                                                           reinterpret_cast<uint32_t *>(e->weights.p));
-      else
-        k_convert_edges<false, uint32_t><<<g, 256, 0, st>>>(nullptr, d_tails64, d_w64, ne, e->tails.p,
-                                                            reinterpret_cast<uint32_t *>(e->weights.p));
-    } else {
-      if (d_aos)
-        k_convert_edges<true, double><<<g, 256, 0, st>>>(d_aos, nullptr, nullptr, ne, e->tails.p,
-                                                         reinterpret_cast<double *>(e->weights.p));
-      else
-        k_convert_edges<false, double><<<g, 256, 0, st>>>(nullptr, d_tails64, d_w64, ne, e->tails.p,
-                                                          reinterpret_cast<double *>(e->weights.p));
-    }
-    e->launches++;
-  }
   // per-vertex / per-community state
   CVB_TRY(e->vdeg.ensure(nvl + 1));
   CVB_TRY(e->cw.ensure(nvl + 1));
@@ -448,6 +413,57 @@ int finish_graph(cvb_engine *e, const void *d_aos, const int64_t *d_tails64, con
   e->graph_ready = true;
   e->phase_ready = false;
   return CVB_OK;
+}
+
+// Everything after the CSR is on the device in boundary layout: pick the
+// weight mode, narrow, compute vertex degrees, build the degree-class lists.
+int finish_graph(cvb_engine *e, const void *d_aos, const int64_t *d_tails64, const double *d_w64) {
+  const int64_t ne = e->ne, nvl = e->nvl;
+  cudaStream_t st = e->stream;
+  CVB_TRY(e->d_flags.ensure(4));
+  CVB_TRY(e->d_sums.ensure(4));
+  CVB_TRY(e->h_sums.ensure(64));
+  CVB_TRY(e->ticket.ensure(4));
+  CVB_TRY(e->partials.ensure(2 * 148 * 16 + 16));
+  CVB_CUDA(cudaMemsetAsync(e->d_flags.p, 0, 4 * sizeof(int), st));
+  CVB_CUDA(cudaMemsetAsync(e->d_sums.p, 0, 4 * sizeof(double), st));
+  CVB_CUDA(cudaMemsetAsync(e->ticket.p, 0, 4 * sizeof(unsigned int), st));
+  if (ne > 0) {
+    if (d_aos)
+      k_weight_stats<true><<<grid_for(ne, 256), 256, 0, st>>>(d_aos, ne, e->d_flags.p, e->d_sums.p);
+    else
+      k_weight_stats<false><<<grid_for(ne, 256), 256, 0, st>>>(d_w64, ne, e->d_flags.p, e->d_sums.p);
+    e->launches++;
+  }
+  int flags = 0;
+  double wsum = 0.0;
+  CVB_CUDA(cudaMemcpyAsync(&flags, e->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CVB_CUDA(cudaMemcpyAsync(&wsum, e->d_sums.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CVB_CUDA(cudaStreamSynchronize(st));
+  e->mode = (flags == 0 && wsum < 4294967296.0) ? CVB_WEIGHTS_U32 : CVB_WEIGHTS_F64;
+  const size_t wbytes = e->mode == CVB_WEIGHTS_U32 ? 4 : 8;
+  CVB_TRY(e->tails.ensure(static_cast<size_t>(ne) + 1));
+  CVB_TRY(e->weights.ensure((static_cast<size_t>(ne) + 1) * wbytes));
+  if (ne > 0) {
+    const int g = grid_for(ne, 256);
+    if (e->mode == CVB_WEIGHTS_U32) {
+      if (d_aos)
+        k_convert_edges<true, uint32_t><<<g, 256, 0, st>>>(d_aos, nullptr, nullptr, ne, e->tails.p,
+                                                           reinterpret_cast<uint32_t *>(e->weights.p));
+      else
+        k_convert_edges<false, uint32_t><<<g, 256, 0, st>>>(nullptr, d_tails64, d_w64, ne, e->tails.p,
+                                                            reinterpret_cast<uint32_t *>(e->weights.p));
+    } else {
+      if (d_aos)
+        k_convert_edges<true, double><<<g, 256, 0, st>>>(d_aos, nullptr, nullptr, ne, e->tails.p,
+                                                         reinterpret_cast<double *>(e->weights.p));
+      else
+        k_convert_edges<false, double><<<g, 256, 0, st>>>(nullptr, d_tails64, d_w64, ne, e->tails.p,
+                                                          reinterpret_cast<double *>(e->weights.p));
+    }
+    e->launches++;
+  }
+  return post_graph(e);
 }
 
 int check_sizes(int64_t nv_local, int64_t base, int64_t nv_global) {
@@ -910,22 +926,205 @@ int cvb_reduce_mod(cvb_engine *e, int64_t nv, const double *local_cdeg, const do
   return CVB_OK;
 }
 
-// ---- coarsening + multi-phase driver (filled in by coarsen.cuh) --------------
-int cvb_coarsen(cvb_engine *e, int64_t *new_nv_out) {
-  (void)e; (void)new_nv_out;
-  set_error("cvb_coarsen: not implemented yet");
-  return CVB_ERR_STATE;
+// ---- coarsening + multi-phase driver -------------------------------------------
+static int coarsen_impl(cvb_engine *e, int64_t *new_nv_out, int32_t *d_compose, int64_t n_compose) {
+  CVB_CHECK(e && e->phase_ready, CVB_ERR_STATE, "cvb_coarsen: run a phase first");
+  CVB_CHECK(e->nvl == e->nvg, CVB_ERR_STATE, "cvb_coarsen is the one-GPU path");
+  CVB_CHECK(e->ne < 2147483000LL, CVB_ERR_CAPACITY, "cvb_coarsen: more than 2^31 entries on one GPU");
+  cudaStream_t st = e->stream;
+  const int64_t nv = e->nvl, ne = e->ne;
+  const vid_t *cvect = e->lab[e->past].p;  // cvect = pastComm, louvain.cpp:741
+  const bool u32 = e->mode == CVB_WEIGHTS_U32;
+  const size_t wbytes = u32 ? 4 : 8;
+  DevBuf<int32_t> first, flag, rank, vnew, head, seg;
+  DevBuf<uint64_t> k_in, k_out;
+  DevBuf<unsigned char> w_out, tmp, nw;
+  DevBuf<int64_t> seg_start, noff;
+  DevBuf<unsigned long long> row_count;
+  DevBuf<vid_t> ntails;
+  auto release = [&]() {
+    first.release(); flag.release(); rank.release(); vnew.release(); head.release(); seg.release();
+    k_in.release(); k_out.release(); w_out.release(); tmp.release(); nw.release(); seg_start.release();
+    noff.release(); row_count.release(); ntails.release();
+  };
+  struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
+  CVB_TRY(first.ensure(nv + 1)); CVB_TRY(flag.ensure(nv + 1)); CVB_TRY(rank.ensure(nv + 2));
+  CVB_TRY(vnew.ensure(nv + 1));
+  // distReNumber: first-appearance numbering
+  k_fill_i32<<<grid_for(nv, 256), 256, 0, st>>>(first.p, nv, 0x7FFFFFFF);
+  k_first_appearance<<<grid_for(nv, 256), 256, 0, st>>>(cvect, nv, first.p);
+  k_flag_first<<<grid_for(nv, 256), 256, 0, st>>>(cvect, first.p, nv, flag.p);
+  e->launches += 3;
+  size_t tb = 0;
+  CVB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.p, rank.p, static_cast<int>(nv), st));
+  size_t tb2 = 0, tb3 = 0, tb4 = 0;
+  if (ne > 0) {
+    CVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb2, (uint64_t *)nullptr, (uint64_t *)nullptr,
+                                             (uint32_t *)nullptr, (uint32_t *)nullptr, static_cast<int>(ne), 0, 64, st));
+    CVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb3, (uint64_t *)nullptr, (uint64_t *)nullptr,
+                                             (double *)nullptr, (double *)nullptr, static_cast<int>(ne), 0, 64, st));
+    CVB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb4, (int32_t *)nullptr, (int32_t *)nullptr,
+                                           static_cast<int>(ne), st));
+  }
+  size_t tbytes = tb;
+  for (size_t x : {tb2, tb3, tb4}) tbytes = x > tbytes ? x : tbytes;
+  CVB_TRY(tmp.ensure(tbytes + 1024));
+  size_t tcap = tmp.cap;
+  CVB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tcap, flag.p, rank.p, static_cast<int>(nv), st));
+  k_vertex_newid<<<grid_for(nv, 256), 256, 0, st>>>(cvect, first.p, rank.p, nv, vnew.p);
+  e->launches += 2;
+  int32_t last_rank = 0, last_flag = 0;
+  CVB_CUDA(cudaMemcpyAsync(&last_rank, rank.p + (nv - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CVB_CUDA(cudaMemcpyAsync(&last_flag, flag.p + (nv - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CVB_CUDA(cudaStreamSynchronize(st));
+  const int64_t nnv = static_cast<int64_t>(last_rank) + last_flag;
+  if (d_compose) {
+    k_compose<<<grid_for(n_compose, 256), 256, 0, st>>>(d_compose, vnew.p, n_compose);
+    e->launches++;
+  }
+  // fill_newEdgesMap: relabel every entry, sort by (src, dst), merge
+  int64_t nne = 0;
+  CVB_TRY(noff.ensure(nnv + 2));
+  CVB_TRY(row_count.ensure(nnv + 2));
+  CVB_CUDA(cudaMemsetAsync(row_count.p, 0, (nnv + 2) * sizeof(unsigned long long), st));
+  if (ne > 0) {
+    CVB_TRY(k_in.ensure(ne)); CVB_TRY(k_out.ensure(ne)); CVB_TRY(w_out.ensure(ne * wbytes));
+    CVB_TRY(head.ensure(ne)); CVB_TRY(seg.ensure(ne));
+    k_edge_keys<<<static_cast<int>((nv * 32 + 255) / 256), 256, 0, st>>>(e->offsets.p, e->tails.p, vnew.p, nv, k_in.p);
+    e->launches++;
+    int bits = 33;  // high word holds src < nnv
+    while ((int64_t(1) << (bits - 32)) < nnv && bits < 64) ++bits;
+    tcap = tmp.cap;
+    if (u32)
+      CVB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tcap, k_in.p, k_out.p, reinterpret_cast<uint32_t *>(e->weights.p),
+                                               reinterpret_cast<uint32_t *>(w_out.p), static_cast<int>(ne), 0, bits, st));
+    else
+      CVB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tcap, k_in.p, k_out.p, reinterpret_cast<double *>(e->weights.p),
+                                               reinterpret_cast<double *>(w_out.p), static_cast<int>(ne), 0, bits, st));
+    k_heads<<<grid_for(ne, 256), 256, 0, st>>>(k_out.p, ne, head.p);
+    tcap = tmp.cap;
+    CVB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tcap, head.p, seg.p, static_cast<int>(ne), st));
+    e->launches += 3;
+    int32_t nseg32 = 0;
+    CVB_CUDA(cudaMemcpyAsync(&nseg32, seg.p + (ne - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(cudaStreamSynchronize(st));
+    nne = nseg32;
+    CVB_TRY(ntails.ensure(nne + 1)); CVB_TRY(seg_start.ensure(nne + 1)); CVB_TRY(nw.ensure((nne + 1) * wbytes));
+    k_emit_entries<<<grid_for(ne, 256), 256, 0, st>>>(k_out.p, head.p, seg.p, ne, ntails.p, seg_start.p, row_count.p);
+    if (u32)
+      k_sum_segments_u32<<<static_cast<int>((nne * 32 + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<uint32_t *>(w_out.p), seg_start.p, nne, ne, reinterpret_cast<uint32_t *>(nw.p));
+    else
+      k_sum_segments_f64<<<grid_for(nne, 256), 256, 0, st>>>(reinterpret_cast<double *>(w_out.p), seg_start.p, nne, ne,
+                                                           reinterpret_cast<double *>(nw.p));
+    e->launches += 2;
+  }
+  // send_newEdges: CSR offsets from the per-row counts
+  size_t tb5 = 0;
+  CVB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb5, (unsigned long long *)nullptr, (int64_t *)nullptr,
+                                         static_cast<int>(nnv + 1), st));
+  CVB_TRY(tmp.ensure(tb5 + 1024));
+  tcap = tmp.cap;
+  CVB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tcap, row_count.p, noff.p, static_cast<int>(nnv + 1), st));
+  e->launches++;
+  // install as the engine's graph
+  e->nvl = e->nvg = nnv;
+  e->base = 0;
+  e->ne = nne;
+  e->graph_ready = false;
+  CVB_TRY(e->offsets.ensure(nnv + 2));
+  CVB_TRY(e->tails.ensure(nne + 1));
+  CVB_TRY(e->weights.ensure((nne + 1) * wbytes));
+  CVB_CUDA(cudaMemcpyAsync(e->offsets.p, noff.p, (nnv + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  if (nne > 0) {
+    CVB_CUDA(cudaMemcpyAsync(e->tails.p, ntails.p, nne * sizeof(vid_t), cudaMemcpyDeviceToDevice, st));
+    CVB_CUDA(cudaMemcpyAsync(e->weights.p, nw.p, nne * wbytes, cudaMemcpyDeviceToDevice, st));
+  }
+  CVB_CUDA(cudaGetLastError());
+  CVB_TRY(post_graph(e));
+  if (new_nv_out) *new_nv_out = nnv;
+  return CVB_OK;
 }
+
+int cvb_coarsen(cvb_engine *e, int64_t *new_nv_out) { return coarsen_impl(e, new_nv_out, nullptr, 0); }
+
 int cvb_graph_download(cvb_engine *e, int64_t *offsets, int64_t *tails, double *weights) {
-  (void)e; (void)offsets; (void)tails; (void)weights;
-  set_error("cvb_graph_download: not implemented yet");
-  return CVB_ERR_STATE;
+  CVB_CHECK(e && e->graph_ready, CVB_ERR_STATE, "no graph");
+  cudaStream_t st = e->stream;
+  if (offsets) CVB_CUDA(cudaMemcpyAsync(offsets, e->offsets.p, (e->nvl + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  if (e->ne > 0 && (tails || weights)) {
+    CVB_TRY(e->staging2.ensure(static_cast<size_t>(e->ne) * 8));
+    if (tails) {
+      int64_t *d64 = reinterpret_cast<int64_t *>(e->staging2.p);
+      k_widen<vid_t, int64_t><<<grid_for(e->ne, 256), 256, 0, st>>>(e->tails.p, d64, e->ne);
+      CVB_CUDA(cudaMemcpyAsync(tails, d64, e->ne * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CVB_CUDA(cudaStreamSynchronize(st));
+      e->launches++;
+    }
+    if (weights) {
+      if (e->mode == CVB_WEIGHTS_U32) {
+        double *d64 = reinterpret_cast<double *>(e->staging2.p);
+        k_widen<uint32_t, double><<<grid_for(e->ne, 256), 256, 0, st>>>(reinterpret_cast<uint32_t *>(e->weights.p), d64, e->ne);
+        e->launches++;
+        CVB_CUDA(cudaMemcpyAsync(weights, d64, e->ne * sizeof(double), cudaMemcpyDeviceToHost, st));
+      } else {
+        CVB_CUDA(cudaMemcpyAsync(weights, e->weights.p, e->ne * sizeof(double), cudaMemcpyDeviceToHost, st));
+      }
+    }
+  }
+  CVB_CUDA(cudaStreamSynchronize(st));
+  return CVB_OK;
 }
+
 int cvb_louvain_run(cvb_engine *e, int max_levels, double *level_q, int *level_iters, int64_t *level_nv,
                     int64_t *comm_out) {
-  (void)e; (void)max_levels; (void)level_q; (void)level_iters; (void)level_nv; (void)comm_out;
-  set_error("cvb_louvain_run: not implemented yet");
-  return CVB_ERR_STATE;
+  if (!e || !e->graph_ready) { set_error("cvb_louvain_run: no graph uploaded"); return CVB_ERR_STATE; }
+  if (e->nvl != e->nvg) { set_error("cvb_louvain_run is the one-GPU driver"); return CVB_ERR_STATE; }
+  cudaStream_t st = e->stream;
+  const int64_t nv0 = e->nvl;
+  DevBuf<int32_t> compose;
+  struct Guard { DevBuf<int32_t> &b; ~Guard() { b.release(); } } guard{compose};
+  if (comm_out && nv0 > 0) {
+    if (compose.ensure(nv0) != CVB_OK) return CVB_ERR_CUDA;
+    k_iota_i32<<<grid_for(nv0, 256), 256, 0, st>>>(compose.p, nv0);
+    e->launches++;
+  }
+  double curr = -1.0, prev = -1.0;  // main.cpp:177
+  int phase = 0, tot_iters = 0;
+  const double threshold = 1.0e-6;  // main.cpp:239
+  while (true) {
+    const int64_t nv = e->nvl;
+    int iters = 0;
+    int rc = cvb_phase_run(e, curr, threshold, 0, &curr, &iters);  // main.cpp:344
+    if (rc != CVB_OK) return rc;
+    tot_iters += iters;
+    if ((curr - prev) > threshold) {  // main.cpp:361
+      rc = coarsen_impl(e, nullptr, comm_out ? compose.p : nullptr, nv0);  // main.cpp:413
+      if (rc != CVB_OK) return rc;
+    } else {
+      break;
+    }
+    if (phase < max_levels) {  // main.cpp:448-450
+      if (level_q) level_q[phase] = curr;
+      if (level_iters) level_iters[phase] = tot_iters;
+      if (level_nv) level_nv[phase] = nv;
+    }
+    prev = curr;
+    curr = -1.0;
+    phase++;
+    if (phase == 200 || tot_iters > 10000) break;  // main.cpp:486
+  }
+  if (comm_out && nv0 > 0) {
+    DevBuf<int64_t> wide;
+    if (wide.ensure(nv0) != CVB_OK) return CVB_ERR_CUDA;
+    k_widen<int32_t, int64_t><<<grid_for(nv0, 256), 256, 0, st>>>(compose.p, wide.p, nv0);
+    e->launches++;
+    cudaError_t err = cudaMemcpyAsync(comm_out, wide.p, nv0 * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    wide.release();
+    if (err != cudaSuccess) { set_error("cvb_louvain_run: D2H failed: %s", cudaGetErrorString(err)); return CVB_ERR_CUDA; }
+  }
+  return phase;
 }
 
 }  // extern "C"
