@@ -1,0 +1,45 @@
+"""torchrun worker: N-GPU phase 0 through cuvite_b200.dist must equal the 1-rank
+reference (golden fixture) bit for bit, and a scale-18 R-MAT phase must equal the oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from cuvite_b200.dist import DistLouvain, init_process_group
+    from cuvite_b200.engine import GpuGraph, set_gpuDevices
+    from cuvite_b200.vite_io import partition_ranges
+    rank, local, world = init_process_group("nccl")
+    set_gpuDevices(local)
+    torch.cuda.set_device(local)
+    stream = torch.cuda.Stream()
+    ok = True
+    with torch.cuda.stream(stream):
+        for name in ("rmat10_intw", "hub30k", "er1k"):
+            g = np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz"))
+            o, t, w = g["offsets"], g["tails"].astype(np.int64), g["weights"]
+            nv = o.size - 1
+            parts = partition_ranges(nv, world)
+            b0, b1 = parts[rank], parts[rank + 1]
+            gpu = GpuGraph(stream=stream.cuda_stream)
+            gpu.upload(o[b0:b1 + 1] - o[b0], t[o[b0]:o[b1]], w[o[b0]:o[b1]], base=b0, nv_global=nv)
+            q, iters = DistLouvain(gpu, rank, world, nv).run_phase()
+            good = iters == int(g["iters"]) and q == float(g["q"]) and np.array_equal(gpu.labels(0), g["cvect"][b0:b1])
+            print(f"rank {rank} {name}: q={q!r} iters={iters} ok={good}", flush=True)
+            ok &= bool(good)
+            gpu.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

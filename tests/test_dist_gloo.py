@@ -1,0 +1,59 @@
+"""World-size > 1 on CPU (gloo): the distributed phase orchestration of
+cuvite_b200.dist (partitioning, delta all-reduce, label all-gather, modularity
+all-reduce, convergence) gives the one-rank reference result for any rank count."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, name, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cuvite_b200.dist import DistLouvain
+    from cuvite_b200.vite_io import partition_ranges
+    from fake_engine import OracleEngine
+    from oracle.binding import Oracle
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz"))
+    o, t, w = g["offsets"], g["tails"].astype(np.int64), g["weights"]
+    nv = o.size - 1
+    parts = partition_ranges(nv, world)
+    b0, b1 = parts[rank], parts[rank + 1]
+    orc = Oracle()
+    orc.set_num_threads(1)
+    eng = OracleEngine(orc).upload(o[b0:b1 + 1] - o[b0], t[o[b0]:o[b1]], w[o[b0]:o[b1]], base=b0, nv_global=nv)
+    dl = DistLouvain(eng, rank, world, nv)
+    q, iters = dl.run_phase()
+    past = eng.tensor("labels_past").numpy()
+    ok = (iters == int(g["iters"]) and abs(q - float(g["q"])) < 1e-12 and np.array_equal(past, g["cvect"][b0:b1]))
+    ret[rank] = (bool(ok), q, iters)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,name", [(2, "rmat10_intw"), (3, "er1k"), (2, "hub30k")])
+def test_distributed_phase_equals_one_rank_reference(oracle, world, name):
+    port = 29600 + world * 7 + len(name)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, name, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert ret[r][0], f"rank {r}: {ret[r]}"
+
+
+def test_partition_ranges_match_reference_formula():
+    from cuvite_b200.vite_io import partition_ranges
+    for nv, p in [(1024, 3), (7, 8), (1 << 20, 8), (30000, 7)]:
+        parts = partition_ranges(nv, p)
+        assert parts[0] == 0 and parts[-1] == nv
+        assert all(parts[i] == (nv * i) // p for i in range(p + 1))  # distgraph.cpp:118-119
