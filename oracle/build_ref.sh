@@ -42,4 +42,15 @@ $CXX $FLAGS "$TMP"/{main,coloring,compare,distgraph,louvain,rebuild,utils}.cpp -
 # harness library: ref_harness.cpp #includes louvain.cpp to reach its statics
 $CXX $FLAGS -fPIC -shared "$HERE/ref_harness.cpp" "$TMP"/{coloring,distgraph,rebuild,utils}.cpp \
      -o "$OUT/libcuvite_ref.so"
+# drop-in proof: the reference's UNMODIFIED main.cpp / louvain.cpp (-DRUNONGPU=1) linked
+# against include/GpuGraph.cuh + cuvite_b200/csrc/adapter.cpp + libcuvite_b200.so
+# instead of its own louvain_cuda.cu / modularity.cu / GpuGraph.cu
+REPO="$(cd "$HERE/.." && pwd)"
+if [ -f "$REPO/cuvite_b200/libcuvite_b200.so" ]; then
+  $CXX $FLAGS -DRUNONGPU=1 -I"$REPO/include" \
+       "$TMP"/{main,coloring,compare,distgraph,louvain,rebuild,utils}.cpp "$REPO/cuvite_b200/csrc/adapter.cpp" \
+       -L"$REPO/cuvite_b200" -lcuvite_b200 -Wl,-rpath,'$ORIGIN/../../cuvite_b200' \
+       -Wl,-rpath,/usr/local/cuda/lib64 -o "$OUT/gc_gpu_dropin"
+  echo "built $OUT/gc_gpu_dropin"
+fi
 echo "built $OUT/gc_cpu64 $OUT/libcuvite_ref.so"

@@ -247,3 +247,34 @@ def test_full_run_rmat18_matches_oracle(gpu, oracle):
     # iteration k's intra-community weight with iteration k+1's degrees and returns the
     # labels of the iteration before (louvain.cpp:521-534, 576) - mirrored, not fixed.
     assert len(np.unique(comm)) == ln[-1] if len(ln) == 1 else len(np.unique(comm)) <= ln[-1]
+
+
+def test_reference_main_runs_on_our_plugin(tmp_path):
+    """The reference's UNMODIFIED main.cpp/louvain.cpp/rebuild.cpp, built with -DRUNONGPU=1
+    against include/GpuGraph.cuh + adapter.cpp + libcuvite_b200.so (oracle/_ref/gc_gpu_dropin),
+    must print the same per-level lines and write the same .communities file as the
+    reference's CPU build (oracle/_ref/gc_cpu64) on the same Vite file."""
+    import os
+    import re
+    import shutil
+    import subprocess
+    from cuvite_b200 import graphgen as gg, vite_io
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    cpu, dropin = os.path.join(ref, "gc_cpu64"), os.path.join(ref, "gc_gpu_dropin")
+    if not (os.path.exists(cpu) and os.path.exists(dropin)):
+        pytest.skip("oracle/_ref binaries not built (needs /root/reference at build time)")
+    g = gg.rmat(14, seed=2)
+    outs = {}
+    for tag, exe in (("cpu", cpu), ("gpu", dropin)):
+        d = tmp_path / tag
+        d.mkdir()
+        f = str(d / "g.bin")
+        vite_io.write_vite(f, g)
+        r = subprocess.run([exe, "-f", f, "-o"], capture_output=True, text=True, timeout=600, cwd=str(d),
+                           env=dict(os.environ, OMP_NUM_THREADS="4"))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        levels = re.findall(r"Level (\d+), Modularity: ([0-9.eE+-]+), Clustering time: [^,]*, Iterations: (\d+)", r.stdout)
+        assert levels, r.stdout[-2000:]
+        outs[tag] = (levels, open(f + ".communities").read())
+    assert outs["cpu"][0] == outs["gpu"][0]
+    assert outs["cpu"][1] == outs["gpu"][1]
