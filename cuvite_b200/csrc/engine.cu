@@ -1,6 +1,7 @@
 // engine.cu — device-resident Louvain phase engine + the C ABI of
 // include/cuvite_b200.h.  One engine = one GPU = one vertex-range partition.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -120,8 +121,12 @@ struct cvb_engine {
   DevBuf<uint2> packed;                 // [nv_global] {label|singleton bit, community degree}
   DevBuf<int64_t> giant_layout;         // chunk_start[ng+1], table_start[ng+1]
   DevBuf<uint32_t> gkeys, gwts, gays, gmeta, gpiece_key;
-  DevBuf<double> gpiece_gain;
+  DevBuf<double> gpiece_gain, gchunk_gain;
+  DevBuf<uint32_t> gchunk_key;
   int64_t giant_chunks = 0, giant_slots = 0;
+  bool use_first_sweep = true; // cvb env CVB_NO_FIRST_SWEEP=1 disables the singleton fast path
+  bool rows_simple = false;    // every row holds each tail at most once (ascending)
+  int sweeps_in_phase = 0;     // 0 right after cvb_phase_begin: all vertices are singletons
   static constexpr int kAux = 4;
   cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr, nullptr};
@@ -216,20 +221,21 @@ int launch_sweep(cvb_engine *e) {
   return CVB_OK;
 }
 
-template <int TPV, int KC, int NCH, int CAP, int VPB>
-int launch_hash(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const vid_t *list, int64_t n,
-                int blocks_per_sm) {
-  const size_t smem = hash_table_bytes<CAP>() * VPB;
+template <int TPV, int KC, int NCH, int MINB>
+int launch_hash(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const vid_t *list, int64_t n) {
+  constexpr int VPB = TPV <= 32 ? 256 / TPV : 1;
+  constexpr int THREADS = TPV <= 32 ? 256 : TPV;
+  const size_t smem = hash_block_smem<TPV, KC, NCH>();
   static bool configured = false;
   if (!configured) {
-    CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_hash<TPV, KC, NCH, CAP, VPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_hash<TPV, KC, NCH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     configured = true;
   }
   int64_t grid = (n + VPB - 1) / VPB;
-  const int64_t cap = static_cast<int64_t>(e->num_sms) * blocks_per_sm;
+  const int64_t cap = static_cast<int64_t>(e->num_sms) * MINB;
   if (grid > cap) grid = cap;
-  k_sweep_u32_hash<TPV, KC, NCH, CAP, VPB><<<static_cast<int>(grid), TPV * VPB, smem, st>>>(p, list, static_cast<int>(n));
+  k_sweep_u32_hash<TPV, KC, NCH, MINB><<<static_cast<int>(grid), THREADS, smem, st>>>(p, list, static_cast<int>(n));
   e->launches++;
   return CVB_OK;
 }
@@ -255,14 +261,55 @@ int launch_sweep_u32(cvb_engine *e) {
   p.dsize = e->dsize.p;
   auto cnt = [&](int c) { return e->class_start[c + 1] - e->class_start[c]; };
   auto lst = [&](int c) { return e->list.p + e->class_start[c]; };
+  int64_t n;
+  if (e->sweeps_in_phase == 0 && e->rows_simple && e->use_first_sweep) {
+    // singleton start: nothing to merge, table-free kernels (one launch per width)
+    auto span = [&](int c0, int c1) { return e->class_start[c1 + 1] - e->class_start[c0]; };
+    CVB_CUDA(cudaEventRecord(e->ev_fork, st));
+    for (int i = 0; i < cvb_engine::kAux; ++i) CVB_CUDA(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
+    auto go = [&](auto kern, int tpv, int c0, int c1, cudaStream_t s2) {
+      const int64_t m = span(c0, c1);
+      if (m <= 0) return;
+      const int vpb = 256 / tpv;
+      int64_t grid = (m + vpb - 1) / vpb;
+      const int64_t cap = static_cast<int64_t>(e->num_sms) * 32;
+      if (grid > cap) grid = cap;
+      kern<<<static_cast<int>(grid), 256, 0, s2>>>(p, lst(c0), static_cast<int>(m));
+      e->launches++;
+    };
+    go(k_sweep_u32_first<256>, 256, kClsH2K, kClsH16K, e->aux[0]);
+    go(k_sweep_u32_first<32>, 32, kClsH256, kClsH1K, e->aux[2]);
+    go(k_sweep_u32_first<8>, 8, kClsG16, kClsH128, e->aux[3]);
+    go(k_sweep_u32_first<1>, 1, kClsG4, kClsG8, e->aux[3]);
+    if ((n = cnt(kClsGiant)) > 0) {
+      GiantTables gt;
+      gt.chunk_start = e->giant_layout.p;
+      gt.table_start = e->giant_layout.p + (n + 1);
+      gt.keys = e->gkeys.p; gt.wts = e->gwts.p; gt.ays = e->gays.p; gt.gmeta = e->gmeta.p;
+      gt.piece_gain = e->gpiece_gain.p; gt.piece_key = e->gpiece_key.p;
+      int64_t g1 = e->giant_chunks < 8LL * e->num_sms ? e->giant_chunks : 8LL * e->num_sms;
+      k_sweep_u32_first_giant<<<static_cast<int>(g1), 512, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt,
+                                                                          e->giant_chunks, e->gchunk_gain.p,
+                                                                          e->gchunk_key.p);
+      k_sweep_u32_first_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(
+          p, lst(kClsGiant), (int)n, gt, e->gchunk_gain.p, e->gchunk_key.p);
+      e->launches += 2;
+    }
+    for (int i = 0; i < cvb_engine::kAux; ++i) {
+      CVB_CUDA(cudaEventRecord(e->ev_join[i], e->aux[i]));
+      CVB_CUDA(cudaStreamWaitEvent(st, e->ev_join[i], 0));
+    }
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
+  }
   CVB_CUDA(cudaEventRecord(e->ev_fork, st));
   for (int i = 0; i < cvb_engine::kAux; ++i) CVB_CUDA(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
-  int64_t n;
-  // stream 0: the block-level hash classes, largest vertices first
-  if ((n = cnt(kClsH16K)) > 0) CVB_TRY((launch_hash<1024, 4, 2, 16384, 1>(e, e->aux[0], p, lst(kClsH16K), n, 1)));
-  if ((n = cnt(kClsH8K)) > 0) CVB_TRY((launch_hash<512, 4, 2, 8192, 1>(e, e->aux[0], p, lst(kClsH8K), n, 2)));
-  if ((n = cnt(kClsH4K)) > 0) CVB_TRY((launch_hash<256, 4, 2, 4096, 1>(e, e->aux[0], p, lst(kClsH4K), n, 4)));
-  if ((n = cnt(kClsH2K)) > 0) CVB_TRY((launch_hash<128, 4, 2, 2048, 1>(e, e->aux[0], p, lst(kClsH2K), n, 8)));
+  // hash classes: 8 CSR entries per thread, TPV = upper degree / 8 threads per vertex
+  // stream 0: block-per-vertex classes, largest vertices first
+  if ((n = cnt(kClsH16K)) > 0) CVB_TRY((launch_hash<1024, 4, 2, 1>(e, e->aux[0], p, lst(kClsH16K), n)));
+  if ((n = cnt(kClsH8K)) > 0) CVB_TRY((launch_hash<512, 4, 2, 2>(e, e->aux[0], p, lst(kClsH8K), n)));
+  if ((n = cnt(kClsH4K)) > 0) CVB_TRY((launch_hash<256, 4, 2, 4>(e, e->aux[0], p, lst(kClsH4K), n)));
+  if ((n = cnt(kClsH2K)) > 0) CVB_TRY((launch_hash<128, 4, 2, 8>(e, e->aux[0], p, lst(kClsH2K), n)));
   // stream 1: giants
   if ((n = cnt(kClsGiant)) > 0) {
     GiantTables gt;
@@ -275,20 +322,26 @@ int launch_sweep_u32(cvb_engine *e) {
     gt.piece_gain = e->gpiece_gain.p;
     gt.piece_key = e->gpiece_key.p;
     const int64_t pieces = e->giant_slots / kGiantPiece;
-    int64_t g1 = e->giant_chunks < 4LL * e->num_sms ? e->giant_chunks : 4LL * e->num_sms;
-    k_sweep_u32_giant_insert<<<static_cast<int>(g1), 512, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt,
-                                                                         e->giant_chunks);
+    int64_t g1 = e->giant_chunks < 2LL * e->num_sms ? e->giant_chunks : 2LL * e->num_sms;
+    constexpr int kGiantSmem = 2 * kGiantChunk * 8;
+    static bool giant_configured = false;
+    if (!giant_configured) {
+      CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_giant_insert, cudaFuncAttributeMaxDynamicSharedMemorySize, kGiantSmem));
+      giant_configured = true;
+    }
+    k_sweep_u32_giant_insert<<<static_cast<int>(g1), 512, kGiantSmem, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt,
+                                                                                  e->giant_chunks);
     int64_t g2 = pieces < 4LL * e->num_sms ? pieces : 4LL * e->num_sms;
     k_sweep_u32_giant_eval<<<static_cast<int>(g2), 512, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt, pieces);
     k_sweep_u32_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n,
                                                                                          gt);
     e->launches += 3;
   }
-  // stream 2: warp-level hash classes
-  if ((n = cnt(kClsH1K)) > 0) CVB_TRY((launch_hash<64, 4, 2, 1024, 1>(e, e->aux[2], p, lst(kClsH1K), n, 16)));
-  if ((n = cnt(kClsH512)) > 0) CVB_TRY((launch_hash<32, 4, 2, 512, 8>(e, e->aux[2], p, lst(kClsH512), n, 4)));
-  if ((n = cnt(kClsH256)) > 0) CVB_TRY((launch_hash<32, 4, 1, 256, 8>(e, e->aux[2], p, lst(kClsH256), n, 8)));
-  if ((n = cnt(kClsH128)) > 0) CVB_TRY((launch_hash<32, 2, 1, 128, 8>(e, e->aux[2], p, lst(kClsH128), n, 8)));
+  // stream 2: warp-level and sub-warp hash classes
+  if ((n = cnt(kClsH1K)) > 0) CVB_TRY((launch_hash<64, 4, 2, 16>(e, e->aux[2], p, lst(kClsH1K), n)));
+  if ((n = cnt(kClsH512)) > 0) CVB_TRY((launch_hash<32, 4, 2, 4>(e, e->aux[2], p, lst(kClsH512), n)));
+  if ((n = cnt(kClsH256)) > 0) CVB_TRY((launch_hash<32, 4, 1, 4>(e, e->aux[2], p, lst(kClsH256), n)));
+  if ((n = cnt(kClsH128)) > 0) CVB_TRY((launch_hash<32, 2, 1, 4>(e, e->aux[2], p, lst(kClsH128), n)));
   // stream 3: the small classes
   if ((n = cnt(kClsG32)) > 0) {
     k_sweep_u32_group<32><<<static_cast<int>((n * 32 + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG32), (int)n);
@@ -387,6 +440,17 @@ int post_graph(cvb_engine *e) {
   }
   if (e->mode == CVB_WEIGHTS_U32) {
     CVB_TRY(e->packed.ensure(e->nvg + 1));
+    CVB_TRY(e->d_flags.ensure(4));
+    CVB_CUDA(cudaMemsetAsync(e->d_flags.p, 0, 4 * sizeof(int), st));
+    if (e->nvl > 0) {
+      k_check_simple_rows<<<static_cast<int>((e->nvl * 32 + 255) / 256), 256, 0, st>>>(e->offsets.p, e->tails.p, e->nvl,
+                                                                                     e->d_flags.p);
+      e->launches++;
+    }
+    int not_simple = 0;
+    CVB_CUDA(cudaMemcpyAsync(&not_simple, e->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(cudaStreamSynchronize(st));
+    e->rows_simple = not_simple == 0;
     if (ngiant > 0) {
       CVB_TRY(e->giant_layout.ensure(2 * (ngiant + 1)));
       k_giant_layout<<<1, 32, 0, st>>>(e->offsets.p, e->list.p + e->class_start[kClsGiant], (int)ngiant,
@@ -405,6 +469,8 @@ int post_graph(cvb_engine *e) {
       CVB_TRY(e->gmeta.ensure(3 * ngiant + 4));
       CVB_TRY(e->gpiece_gain.ensure(e->giant_slots / kGiantPiece + 1));
       CVB_TRY(e->gpiece_key.ensure(e->giant_slots / kGiantPiece + 1));
+      CVB_TRY(e->gchunk_gain.ensure(e->giant_chunks + 1));
+      CVB_TRY(e->gchunk_key.ensure(e->giant_chunks + 1));
       CVB_CUDA(cudaMemsetAsync(e->gkeys.p, 0xFF, e->giant_slots * sizeof(uint32_t), st));
       CVB_CUDA(cudaMemsetAsync(e->gwts.p, 0, e->giant_slots * sizeof(uint32_t), st));
       CVB_CUDA(cudaMemsetAsync(e->gmeta.p, 0, (3 * ngiant + 4) * sizeof(uint32_t), st));
@@ -507,6 +573,7 @@ cvb_engine *cvb_create(void *stream) {
   }
   cvb_engine *e = new cvb_engine;
   e->device = dev;
+  if (const char *s = getenv("CVB_NO_FIRST_SWEEP")) e->use_first_sweep = !(s[0] == '1');
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) e->num_sms = sms;
   if (stream) {
@@ -548,7 +615,8 @@ void cvb_destroy(cvb_engine *e) {
   e->partials.release(); e->d_sums.release(); e->ticket.release(); e->d_flags.release();
   e->h_sums.release(); e->staging.release(); e->staging2.release(); e->giant.release(); e->h_stage.release();
   e->packed.release(); e->giant_layout.release(); e->gkeys.release(); e->gwts.release(); e->gays.release();
-  e->gmeta.release(); e->gpiece_key.release(); e->gpiece_gain.release();
+  e->gmeta.release(); e->gpiece_key.release(); e->gpiece_gain.release(); e->gchunk_gain.release();
+  e->gchunk_key.release();
   for (int i = 0; i < cvb_engine::kAux; ++i) {
     if (e->aux[i]) cudaStreamDestroy(e->aux[i]);
     if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
@@ -645,6 +713,7 @@ int cvb_phase_begin(cvb_engine *e, double total_weight) {
   CVB_CUDA(cudaGetLastError());
   e->phase_ready = true;
   e->sweep_timed = false;
+  e->sweeps_in_phase = 0;
   return CVB_OK;
 }
 
@@ -659,6 +728,7 @@ int cvb_sweep(cvb_engine *e) {
     CVB_TRY(launch_sweep<double>(e));
   CVB_CUDA(cudaEventRecord(e->ev1, e->stream));
   e->sweep_timed = true;
+  e->sweeps_in_phase++;
   return CVB_OK;
 }
 
@@ -852,6 +922,7 @@ int cvb_louvain_iteration(cvb_engine *e, int64_t nv, int64_t base, int64_t nv_gl
       e->launches++;
     }
   }
+  e->sweeps_in_phase = 1;  // caller-provided labels: never the singleton fast path
   CVB_TRY(cvb_sweep(e));
   // outputs: [target 8nv][dsize 8nv][ddeg 8nv][rsize 8nr][rdeg 8nr]
   const size_t need2 = static_cast<size_t>(nv) * 24 + static_cast<size_t>(n_rcomm) * 16 + 64;

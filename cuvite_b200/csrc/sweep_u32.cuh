@@ -208,11 +208,13 @@ __global__ void __launch_bounds__(256) k_sweep_u32_group(SweepU32Params p, const
 // community's gain after the last insert, then frees the slot — so there is no
 // per-table list and no table scan, and the cost after the insert phase is
 // proportional to the number of distinct neighbour communities.
-// Per table: keys[CAP] wts[CAP] ays[CAP] (uint32), meta[4] = {-, selfloop, counter0, -}.
+// Per table: keys[CAP] wts[CAP] (uint32), meta[4] = {-, selfloop, counter0, -}.
 // ---------------------------------------------------------------------------
-template <int CAP>
-__host__ __device__ constexpr size_t hash_table_bytes() {
-  return static_cast<size_t>(CAP) * 12 + 16;
+// dynamic shared memory of one block of k_sweep_u32_hash<TPV, KC, NCH>
+template <int TPV, int KC, int NCH>
+__host__ __device__ constexpr size_t hash_block_smem() {
+  return (TPV <= 32) ? static_cast<size_t>(256 / TPV) * (2 * KC * NCH * TPV) * 8
+                     : static_cast<size_t>(2 * KC * NCH * TPV) * 8 + 16;
 }
 
 template <int TPV>
@@ -227,20 +229,19 @@ __device__ __forceinline__ void tile_sync() {
 // REDUX operations: positive doubles order like their bit patterns.
 // Returns the winning key (singleton bit included) or kLabelMask when no lane
 // holds a positive gain; *gain_out gets the winning gain (or -1).
-__device__ __forceinline__ uint32_t warp_argmax(double g, uint32_t key, double *gain_out) {
+__device__ __forceinline__ uint32_t warp_argmax(double g, uint32_t key, double *gain_out,
+                                                unsigned gmask = 0xffffffffu) {
   const unsigned long long gb = (g > 0.0) ? static_cast<unsigned long long>(__double_as_longlong(g)) : 0ull;
   const uint32_t hi = static_cast<uint32_t>(gb >> 32), lo = static_cast<uint32_t>(gb);
-  const uint32_t mhi = __reduce_max_sync(0xffffffffu, hi);
-  const uint32_t mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  const uint32_t mhi = __reduce_max_sync(gmask, hi);
+  const uint32_t mlo = __reduce_max_sync(gmask, hi == mhi ? lo : 0u);
   const bool top = gb != 0ull && hi == mhi && lo == mlo;
-  const uint32_t mid = __reduce_min_sync(0xffffffffu, top ? (key & kLabelMask) : 0xFFFFFFFFu);
-  const unsigned who = __ballot_sync(0xffffffffu, top && (key & kLabelMask) == mid);
-  if (who == 0u) {
-    *gain_out = -1.0;
-    return kLabelMask;
-  }
-  *gain_out = __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(mhi) << 32) | mlo));
-  return __shfl_sync(0xffffffffu, key, __ffs(who) - 1);
+  const uint32_t mid = __reduce_min_sync(gmask, top ? (key & kLabelMask) : 0xFFFFFFFFu);
+  const unsigned who = __ballot_sync(gmask, top && (key & kLabelMask) == mid);
+  *gain_out = (who == 0u) ? -1.0
+                          : __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(mhi) << 32) | mlo));
+  const uint32_t wkey = __shfl_sync(gmask, key, who ? (__ffs(who) - 1) : 0);
+  return who ? wkey : kLabelMask;
 }
 
 // Shared-memory accesses by 32-bit shared address (one address register +
@@ -275,31 +276,61 @@ __device__ __forceinline__ uint32_t hash_step(uint32_t key, int log2cap) {
   return ((((key & kLabelMask) * 0x85EBCA6Bu) >> (32 - log2cap)) | 1u);
 }
 
+// Reductions over the GL contiguous lanes of one vertex.  GL == 32 uses REDUX;
+// smaller groups use xor shuffles (REDUX with a per-group mask makes ptxas
+// emit a match.any loop over the distinct masks).
+template <int GL>
+__device__ __forceinline__ uint32_t group_sum(uint32_t v, unsigned gmask) {
+  if (GL == 32) return __reduce_add_sync(0xffffffffu, v);
+#pragma unroll
+  for (int o = GL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+
+template <int GL>
+__device__ __forceinline__ uint32_t group_argmax(double g, uint32_t key, double *gain_out, unsigned gmask) {
+  if (GL == 32) return warp_argmax(g, key, gain_out, 0xffffffffu);
+#pragma unroll
+  for (int o = GL / 2; o > 0; o >>= 1) {
+    const double g2 = __shfl_xor_sync(gmask, g, o);
+    const uint32_t k2 = __shfl_xor_sync(gmask, key, o);
+    if (better_u(g2, k2, g, key)) {
+      g = g2;
+      key = k2;
+    }
+  }
+  *gain_out = g;
+  return key;
+}
+
 // Insert KC entries per lane into the open-addressing table.  kaddr is the
-// shared address of keys[]; wts[] and ays[] follow at +capb and +2*capb bytes.
-// All KC first-probe claims are issued back to back (independent shared-memory
-// atomics in flight); a collided entry then walks its own short probe loop
-// (double hashing).  Bit k of the return value is set when this lane claimed a
-// fresh slot for entry k; slb[k] is the entry's final slot as a BYTE offset.
+// shared address of keys[]; wts[] follows at +capb bytes.  All KC first-probe
+// claims are issued back to back (independent shared-memory atomics in flight);
+// a collided entry then walks its own short probe loop (double hashing).  Bit k
+// of the return value is set when this lane claimed a fresh slot for entry k;
+// slb[k] is the entry's final slot as a BYTE offset.
 template <int KC>
 __device__ __forceinline__ uint32_t table_insert_chunk(uint32_t kaddr, uint32_t capb, const uint32_t (&key)[KC],
-                                                       const uint32_t (&ay)[KC], const uint32_t (&w)[KC],
-                                                       uint32_t active, int log2cap, uint32_t maskb,
-                                                       uint32_t (&slb)[KC]) {
+                                                       const uint32_t (&w)[KC], uint32_t active, int log2cap,
+                                                       uint32_t maskb, uint32_t (&slb)[KC]) {
   uint32_t old[KC];
-  uint32_t fresh = 0u;
+  uint32_t fresh = 0u, pend = 0u;
 #pragma unroll
   for (int k = 0; k < KC; ++k) {
     slb[k] = hash_key(key[k], log2cap) << 2;
-    old[k] = kEmptyKeyU;
+    old[k] = key[k];
     if (active & (1u << k)) old[k] = atoms_cas(kaddr + slb[k], kEmptyKeyU, key[k]);
   }
 #pragma unroll
-  for (int k = 0; k < KC; ++k)
-    if (active & (1u << k)) {
-      if (old[k] == kEmptyKeyU) {
-        fresh |= 1u << k;
-      } else if (old[k] != key[k]) {
+  for (int k = 0; k < KC; ++k) {
+    const bool act = (active >> k) & 1u;
+    fresh |= (act && old[k] == kEmptyKeyU) ? (1u << k) : 0u;
+    pend |= (act && old[k] != kEmptyKeyU && old[k] != key[k]) ? (1u << k) : 0u;
+  }
+  if (pend) {  // collided first probes: rare lanes, short loops
+#pragma unroll
+    for (int k = 0; k < KC; ++k)
+      if (pend & (1u << k)) {
         const uint32_t step = hash_step(key[k], log2cap) << 2;
         while (true) {
           slb[k] = (slb[k] + step) & maskb;
@@ -311,133 +342,178 @@ __device__ __forceinline__ uint32_t table_insert_chunk(uint32_t kaddr, uint32_t 
           if (o == key[k]) break;
         }
       }
-    }
+  }
 #pragma unroll
   for (int k = 0; k < KC; ++k)
-    if (active & (1u << k)) {
-      reds_add(kaddr + capb + slb[k], w[k]);
-      if (fresh & (1u << k)) sts_u32(kaddr + 2u * capb + slb[k], ay[k]);
-    }
+    if (active & (1u << k)) reds_add(kaddr + capb + slb[k], w[k]);
   return fresh;
 }
 
-// K = KC * NCH entries per thread, processed in NCH chunks of KC.
-template <int TPV, int KC, int NCH, int CAP, int VPB>
-__global__ void __launch_bounds__(TPV *VPB) k_sweep_u32_hash(SweepU32Params p, const vid_t *__restrict__ list, int n) {
+struct VertexHeader {
+  vid_t v;
+  eid_t e0, e1;
+  uint2 me;
+  double vd;
+};
+
+__device__ __forceinline__ VertexHeader fetch_header(const SweepU32Params &p, vid_t v) {
+  VertexHeader h;
+  h.v = v;
+  h.e0 = p.offsets[v];
+  h.e1 = p.offsets[v + 1];
+  h.me = p.packed[v + p.base];
+  h.vd = p.vdeg[v];
+  return h;
+}
+
+// K = KC * NCH entries per thread, processed in NCH chunks of KC; the table of a
+// vertex has 2*K*TPV slots.  TPV < 32: 32/TPV vertices share a warp (lanes of a
+// vertex are contiguous; every collective carries the vertex's lane mask), so
+// the per-vertex bookkeeping instructions are issued once for several
+// vertices; TPV >= 64: one block per vertex.
+template <int TPV, int KC, int NCH, int MINB>
+__global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
+    k_sweep_u32_hash(SweepU32Params p, const vid_t *__restrict__ list, int n) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
   __shared__ double red_g[32];
   __shared__ uint32_t red_id[32];
   constexpr int kWarpsPerVertex = TPV / 32;
+  constexpr int K = KC * NCH;
+  constexpr int CAP = 2 * K * TPV;  // slots per vertex (power of two)
+  constexpr int VPB = TPV <= 32 ? 256 / TPV : 1;
+  constexpr int GL = TPV < 32 ? TPV : 32;  // lanes of one vertex inside a warp
   constexpr uint32_t capb = CAP * 4u;
-  constexpr int kWords = CAP * 3 + 4;
+  constexpr int kWords = CAP * 2 + (TPV > 32 ? 4 : 0);
   const unsigned lane = threadIdx.x & 31u;
-  const int tid = (TPV == 32) ? static_cast<int>(lane) : static_cast<int>(threadIdx.x);
-  const int vslot = (TPV == 32) ? static_cast<int>(threadIdx.x >> 5) : 0;
-  const int wiv = (TPV == 32) ? 0 : static_cast<int>(threadIdx.x >> 5);  // warp in vertex
+  const unsigned gmask = (GL == 32) ? 0xffffffffu : (((1u << GL) - 1u) << (lane & ~static_cast<unsigned>(GL - 1)));
+  const int tid = (TPV <= 32) ? static_cast<int>(threadIdx.x & (TPV - 1)) : static_cast<int>(threadIdx.x);
+  const int vslot = (TPV <= 32) ? static_cast<int>(threadIdx.x / TPV) : 0;
+  const int wiv = (TPV <= 32) ? 0 : static_cast<int>(threadIdx.x >> 5);  // warp in vertex
   uint32_t *keys = smem_u32 + kWords * vslot;
   uint32_t *wts = keys + CAP;
-  uint32_t *meta = keys + 3 * CAP;
+  uint32_t *meta = keys + 2 * CAP;  // only for TPV > 32
   const uint32_t kaddr = smem_addr(keys);
   for (int s = tid; s < CAP; s += TPV) {
     keys[s] = kEmptyKeyU;
     wts[s] = 0u;
   }
-  if (tid < 4) meta[tid] = 0u;
-  tile_sync<TPV>();
+  if (TPV > 32) {
+    if (tid < 4) meta[tid] = 0u;
+    __syncthreads();
+  } else {
+    __syncwarp(gmask);
+  }
 
-  for (int64_t item = static_cast<int64_t>(blockIdx.x) * VPB + vslot; item < n;
-       item += static_cast<int64_t>(gridDim.x) * VPB) {
-    const vid_t v = list[item];
-    const eid_t e0 = p.offsets[v], e1 = p.offsets[v + 1];
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * VPB;
+  int64_t item = static_cast<int64_t>(blockIdx.x) * VPB + vslot;
+  if (item >= n) return;  // all lanes of a vertex leave together
+  // two-deep software pipeline over the class list: the id of vertex i+2 and the
+  // header (offsets, own packed entry, degree) of vertex i+1 are in flight
+  // while vertex i is processed
+  VertexHeader hc = fetch_header(p, list[item]);
+  vid_t v_next = (item + stride < n) ? list[item + stride] : -1;
+  for (; item < n; item += stride) {
+    VertexHeader hn = hc;
+    if (v_next >= 0) hn = fetch_header(p, v_next);
+    const vid_t v_next2 = (item + 2 * stride < n) ? list[item + 2 * stride] : -1;
+
+    const vid_t v = hc.v;
+    const eid_t e0 = hc.e0, e1 = hc.e1;
     const int deg = static_cast<int>(e1 - e0);
     const vid_t self = v + p.base;
-    const uint2 me = p.packed[self];
+    const uint2 me = hc.me;
     const uint32_t cc = me.x & kLabelMask;
-    const double vd = p.vdeg[v];
+    const double vd = hc.vd;
     int log2cap = 32 - __clz(2 * deg - 1);  // ceil(log2(2*deg)): load factor <= 0.5
-    log2cap = log2cap < 6 ? 6 : (log2cap > 31 - __clz(CAP) ? 31 - __clz(CAP) : log2cap);
+    log2cap = log2cap < 4 ? 4 : (log2cap > 31 - __clz(CAP) ? 31 - __clz(CAP) : log2cap);
     const uint32_t maskb = ((1u << log2cap) - 1u) << 2;
 
-    uint16_t claimed[NCH][KC];  // byte offsets / 4 of the slots this lane claimed
-    uint32_t freshmask = 0u, ownsum = 0u;
+    // claims of this lane: key, community degree and slot of every entry that
+    // opened a new table slot (valid where the fresh bit is set)
+    uint32_t ckey[K], cay[K];
+    uint16_t cslot[K];
+    uint32_t freshmask = 0u, ownsum = 0u, selfsum = 0u;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      if (c * KC * TPV < deg) {  // tile-uniform
-        uint32_t key[KC], ay[KC], w[KC], slb[KC];
+      {  // every class spans (K*TPV/2, K*TPV] entries, so all chunks are populated
+        uint32_t key[KC], w[KC], slb[KC];
         vid_t tail[KC];
+        uint32_t validm = 0u;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
           const eid_t e = e0 + tid + static_cast<eid_t>(c * KC + k) * TPV;
-          tail[k] = -1;
+          tail[k] = self;  // a safe address for the gather of idle lanes
           w[k] = 0u;
           if (e < e1) {
             tail[k] = p.tails[e];
             w[k] = p.weights[e];
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < KC; ++k) {
-          key[k] = kEmptyKeyU;
-          ay[k] = 0u;
-          if (tail[k] >= 0) {
-            const uint2 pk = p.packed[tail[k]];
-            key[k] = pk.x;
-            ay[k] = pk.y;
+            validm |= 1u << k;
           }
         }
         uint32_t active = 0u;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
-          const bool valid = tail[k] >= 0;
-          if (valid && tail[k] == self) atomicAdd(&meta[1], w[k]);
-          const bool own = valid && (key[k] & kLabelMask) == cc;
-          if (own) ownsum += w[k];
-          if (valid && !own) active |= 1u << k;
+          const uint2 pk = p.packed[tail[k]];
+          const bool valid = (validm >> k) & 1u;
+          key[k] = valid ? pk.x : kEmptyKeyU;
+          cay[c * KC + k] = pk.y;
+          const bool own = (key[k] & kLabelMask) == cc;  // idle lanes: 0x7fffffff is never a label
+          ownsum += own ? w[k] : 0u;
+          selfsum += (valid && tail[k] == self) ? w[k] : 0u;
+          active |= (valid && !own) ? (1u << k) : 0u;
         }
-        const uint32_t fresh = table_insert_chunk<KC>(kaddr, capb, key, ay, w, active, log2cap, maskb, slb);
+        const uint32_t fresh = table_insert_chunk<KC>(kaddr, capb, key, w, active, log2cap, maskb, slb);
         freshmask |= fresh << (c * KC);
 #pragma unroll
-        for (int k = 0; k < KC; ++k) claimed[c][k] = static_cast<uint16_t>(slb[k] >> 2);
+        for (int k = 0; k < KC; ++k) {
+          ckey[c * KC + k] = key[k];
+          cslot[c * KC + k] = static_cast<uint16_t>(slb[k] >> 2);
+        }
       }
     }
-    {  // own-community weight: one REDUX + one atomic per warp
-      const uint32_t s = __reduce_add_sync(0xffffffffu, ownsum);
-      if (lane == 0 && s) atomicAdd(&meta[2], s);
+    // own-community weight and self-loop weight of the vertex
+    uint32_t c0u = ownsum, slu = selfsum;
+    if (TPV > 1) {
+      c0u = group_sum<GL>(ownsum, gmask);
+      slu = group_sum<GL>(selfsum, gmask);
     }
-    tile_sync<TPV>();
+    if (TPV > 32) {
+      if (lane == 0) {
+        if (c0u) atomicAdd(&meta[2], c0u);
+        if (slu) atomicAdd(&meta[1], slu);
+      }
+      __syncthreads();
+      c0u = meta[2];
+      slu = meta[1];
+    } else {
+      __syncwarp(gmask);
+    }
 
     // ---- evaluate: the claimer of each key reads its total and frees the slot ----
-    const double counter0 = static_cast<double>(meta[2]);
-    const double eix = counter0 - static_cast<double>(meta[1]);
+    const double counter0 = static_cast<double>(c0u);
+    const double eix = counter0 - static_cast<double>(slu);
     const double ax = static_cast<double>(me.y) - vd;
     double g = -1.0;
     uint32_t id = kLabelMask;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c)
-#pragma unroll
-      for (int k = 0; k < KC; ++k)
-        if (freshmask & (1u << (c * KC + k))) {
-          const uint32_t a = kaddr + (static_cast<uint32_t>(claimed[c][k]) << 2);
-          const uint32_t kk = lds_u32(a);
-          const uint32_t tot = lds_u32(a + capb);
-          const uint32_t ayv = lds_u32(a + 2u * capb);
-          sts_u32(a, kEmptyKeyU);
-          sts_u32(a + capb, 0u);
-          const double g2 = modularity_gain(static_cast<double>(tot), eix, vd, static_cast<double>(ayv), ax, p.constant);
-          if (better_u(g2, kk, g, id)) {
-            g = g2;
-            id = kk;
-          }
+    for (int q = 0; q < K; ++q)
+      if (freshmask & (1u << q)) {
+        const uint32_t a = kaddr + (static_cast<uint32_t>(cslot[q]) << 2);
+        const uint32_t tot = lds_u32(a + capb);
+        sts_u32(a, kEmptyKeyU);
+        sts_u32(a + capb, 0u);
+        const double g2 = modularity_gain(static_cast<double>(tot), eix, vd, static_cast<double>(cay[q]), ax, p.constant);
+        if (better_u(g2, ckey[q], g, id)) {
+          g = g2;
+          id = ckey[q];
         }
-    double wg;
-    uint32_t wid = warp_argmax(g, id, &wg);
-    if (TPV == 32) {
-      if (lane == 0) {
-        commit_vertex_u32(p, v, me.x, wg, wid, vd, counter0);
-        meta[1] = 0u;
-        meta[2] = 0u;
       }
-      __syncwarp();
+    double wg = g;
+    uint32_t wid = id;
+    if (TPV > 1) wid = group_argmax<GL>(g, id, &wg, gmask);
+    if (TPV <= 32) {
+      if (tid == 0) commit_vertex_u32(p, v, me.x, wg, wid, vd, counter0);
+      __syncwarp(gmask);
     } else {
       if (lane == 0) {
         red_g[wiv] = wg;
@@ -456,6 +532,8 @@ __global__ void __launch_bounds__(TPV *VPB) k_sweep_u32_hash(SweepU32Params p, c
       }
       __syncthreads();
     }
+    hc = hn;
+    v_next = v_next2;
   }
 }
 
@@ -511,65 +589,151 @@ __device__ __forceinline__ int giant_owner(const int64_t *__restrict__ start, in
   return lo;
 }
 
-__global__ void __launch_bounds__(512) k_sweep_u32_giant_insert(SweepU32Params p, const vid_t *__restrict__ list, int n,
-                                                               GiantTables gt, int64_t total_chunks) {
-  constexpr int KG = kGiantChunk / 512;  // entries per thread per chunk
+// Global-table twin of table_insert_chunk: K independent L2 atomics in flight,
+// collided entries retry in their own short loops.
+template <int K>
+__device__ __forceinline__ void gtable_insert_chunk(uint32_t *__restrict__ keys, uint32_t *__restrict__ wts,
+                                                    uint32_t *__restrict__ ays, const uint32_t (&key)[K],
+                                                    const uint32_t (&ay)[K], const uint32_t (&w)[K], uint32_t active,
+                                                    int log2cap, uint32_t mask) {
+  uint32_t old[K], sl[K];
+  uint32_t fresh = 0u, pend = 0u;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    sl[k] = hash_key(key[k], log2cap);
+    old[k] = key[k];
+    if (active & (1u << k)) old[k] = atomicCAS(&keys[sl[k]], kEmptyKeyU, key[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const bool act = (active >> k) & 1u;
+    fresh |= (act && old[k] == kEmptyKeyU) ? (1u << k) : 0u;
+    pend |= (act && old[k] != kEmptyKeyU && old[k] != key[k]) ? (1u << k) : 0u;
+  }
+  // collided entries: every round issues ALL outstanding claims back to back, so a
+  // round costs one L2 round trip however many entries are still pending
+  while (pend) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (pend & (1u << k)) {
+        sl[k] = (sl[k] + hash_step(key[k], log2cap)) & mask;
+        old[k] = atomicCAS(&keys[sl[k]], kEmptyKeyU, key[k]);
+      }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (pend & (1u << k)) {
+        if (old[k] == kEmptyKeyU) {
+          fresh |= 1u << k;
+          pend &= ~(1u << k);
+        } else if (old[k] == key[k]) {
+          pend &= ~(1u << k);
+        }
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+    if (active & (1u << k)) {
+      atomicAdd(&wts[sl[k]], w[k]);
+      if (fresh & (1u << k)) ays[sl[k]] = ay[k];
+    }
+}
+
+// One 4096-entry chunk per block iteration: the chunk is first merged in a
+// shared-memory table (cheap atomics; duplicates collapse), then each claiming
+// lane flushes its distinct (community, weight, degree) triples into the
+// vertex's global table — so the number of L2 atomics is the number of distinct
+// communities per chunk, and they are issued with 8 independent ones in flight.
+__global__ void __launch_bounds__(512, 2) k_sweep_u32_giant_insert(SweepU32Params p, const vid_t *__restrict__ list,
+                                                                  int n, GiantTables gt, int64_t total_chunks) {
+  constexpr int TPV = 512, KC = 4, NCH = kGiantChunk / (TPV * KC), K = KC * NCH;
+  constexpr int CAP = 2 * kGiantChunk;
+  constexpr uint32_t capb = CAP * 4u;
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  uint32_t *skeys = smem_u32, *swts = smem_u32 + CAP;
+  const uint32_t kaddr = smem_addr(skeys);
   const unsigned lane = threadIdx.x & 31u;
+  const int tid = threadIdx.x;
+  for (int s = tid; s < CAP; s += TPV) {
+    skeys[s] = kEmptyKeyU;
+    swts[s] = 0u;
+  }
+  __syncthreads();
+  constexpr int log2cap_s = 13;  // CAP = 8192
+  constexpr uint32_t maskb = (CAP - 1u) << 2;
   for (int64_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     const int gi = giant_owner(gt.chunk_start, n, chunk);
     const vid_t v = list[gi];
-    const eid_t e0 = p.offsets[v], e1 = p.offsets[v + 1];
-    const eid_t c0e = e0 + (chunk - gt.chunk_start[gi]) * kGiantChunk;
-    const eid_t c1e = (c0e + kGiantChunk < e1) ? c0e + kGiantChunk : e1;
+    const eid_t ve0 = p.offsets[v], ve1 = p.offsets[v + 1];
+    const eid_t e0 = ve0 + (chunk - gt.chunk_start[gi]) * kGiantChunk;
+    const eid_t e1 = (e0 + kGiantChunk < ve1) ? e0 + kGiantChunk : ve1;
     const vid_t self = v + p.base;
     const uint32_t cc = p.packed[self].x & kLabelMask;
     const int64_t tbase = gt.table_start[gi];
-    const int64_t cap = gt.table_start[gi + 1] - tbase;
-    const int log2cap = 63 - __clzll(cap);
-    const uint32_t mask = static_cast<uint32_t>(cap - 1);
-    uint32_t *keys = gt.keys + tbase, *wts = gt.wts + tbase, *ays = gt.ays + tbase;
+    const int64_t gcap = gt.table_start[gi + 1] - tbase;
+    const int glog2 = 63 - __clzll(gcap);
+    const uint32_t gmask = static_cast<uint32_t>(gcap - 1);
     uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
-    vid_t tail[KG];
-    uint32_t w[KG];
-    uint2 pk[KG];
+
+    uint32_t ckey[K], cay[K];
+    uint16_t cslot[K];
+    uint32_t freshmask = 0u, ownsum = 0u, selfsum = 0u;
 #pragma unroll
-    for (int k = 0; k < KG; ++k) {
-      const eid_t e = c0e + threadIdx.x + static_cast<eid_t>(k) * 512;
-      tail[k] = -1;
-      w[k] = 0u;
-      if (e < c1e) {
-        tail[k] = p.tails[e];
-        w[k] = p.weights[e];
-      }
-    }
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t key[KC], w[KC], slb[KC];
+      vid_t tail[KC];
+      uint32_t validm = 0u;
 #pragma unroll
-    for (int k = 0; k < KG; ++k) {
-      pk[k] = make_uint2(kEmptyKeyU, 0u);
-      if (tail[k] >= 0) pk[k] = p.packed[tail[k]];
-    }
-    uint32_t ownsum = 0u;
-#pragma unroll
-    for (int k = 0; k < KG; ++k) {
-      const bool valid = tail[k] >= 0;
-      if (valid && tail[k] == self) atomicAdd(&meta[1], w[k]);
-      const bool own = valid && (pk[k].x & kLabelMask) == cc;
-      if (own) ownsum += w[k];
-      if (valid && !own) {
-        uint32_t slot = hash_key(pk[k].x, log2cap);
-        while (true) {
-          const uint32_t old = atomicCAS(&keys[slot], kEmptyKeyU, pk[k].x);
-          if (old == kEmptyKeyU) {
-            ays[slot] = pk[k].y;
-            break;
-          }
-          if (old == pk[k].x) break;
-          slot = (slot + 1u) & mask;
+      for (int k = 0; k < KC; ++k) {
+        const eid_t e = e0 + tid + static_cast<eid_t>(c * KC + k) * TPV;
+        tail[k] = self;
+        w[k] = 0u;
+        if (e < e1) {
+          tail[k] = p.tails[e];
+          w[k] = p.weights[e];
+          validm |= 1u << k;
         }
-        atomicAdd(&wts[slot], w[k]);
+      }
+      uint32_t active = 0u;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const uint2 pk = p.packed[tail[k]];
+        const bool valid = (validm >> k) & 1u;
+        key[k] = valid ? pk.x : kEmptyKeyU;
+        cay[c * KC + k] = pk.y;
+        const bool own = (key[k] & kLabelMask) == cc;
+        ownsum += own ? w[k] : 0u;
+        selfsum += (valid && tail[k] == self) ? w[k] : 0u;
+        active |= (valid && !own) ? (1u << k) : 0u;
+      }
+      const uint32_t fresh = table_insert_chunk<KC>(kaddr, capb, key, w, active, log2cap_s, maskb, slb);
+      freshmask |= fresh << (c * KC);
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        ckey[c * KC + k] = key[k];
+        cslot[c * KC + k] = static_cast<uint16_t>(slb[k] >> 2);
       }
     }
-    const uint32_t s = __reduce_add_sync(0xffffffffu, ownsum);
-    if (lane == 0 && s) atomicAdd(&meta[2], s);
+    const uint32_t c0u = __reduce_add_sync(0xffffffffu, ownsum);
+    const uint32_t slu = __reduce_add_sync(0xffffffffu, selfsum);
+    if (lane == 0) {
+      if (c0u) atomicAdd(&meta[2], c0u);
+      if (slu) atomicAdd(&meta[1], slu);
+    }
+    __syncthreads();
+    // flush this lane's claims: chunk totals -> global table
+    uint32_t tot[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+      tot[q] = 0u;
+      if (freshmask & (1u << q)) {
+        const uint32_t a = kaddr + (static_cast<uint32_t>(cslot[q]) << 2);
+        tot[q] = lds_u32(a + capb);
+        sts_u32(a, kEmptyKeyU);
+        sts_u32(a + capb, 0u);
+      }
+    }
+    gtable_insert_chunk<K>(gt.keys + tbase, gt.wts + tbase, gt.ays + tbase, ckey, cay, tot, freshmask, glog2, gmask);
+    __syncthreads();
   }
 }
 
@@ -595,16 +759,29 @@ __global__ void __launch_bounds__(512) k_sweep_u32_giant_eval(SweepU32Params p, 
 #pragma unroll
     for (int j = 0; j < kGiantPiece / 512; ++j) k[j] = __ldcg(&gt.keys[s0 + threadIdx.x + j * 512]);
 #pragma unroll
-    for (int j = 0; j < kGiantPiece / 512; ++j) {
-      if (k[j] != kEmptyKeyU) {
-        const int64_t s = s0 + threadIdx.x + j * 512;
-        const double g2 = modularity_gain(static_cast<double>(__ldcg(&gt.wts[s])), eix, vd,
-                                          static_cast<double>(__ldcg(&gt.ays[s])), ax, p.constant);
-        gt.keys[s] = kEmptyKeyU;
-        gt.wts[s] = 0u;
-        if (better_u(g2, k[j], g, id)) {
-          g = g2;
-          id = k[j];
+    for (int j0 = 0; j0 < kGiantPiece / 512; j0 += 4) {  // 4 slots' dependent loads in flight together
+      uint32_t wv[4], av[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        wv[j] = 0u;
+        av[j] = 0u;
+        if (k[j0 + j] != kEmptyKeyU) {
+          const int64_t s = s0 + threadIdx.x + (j0 + j) * 512;
+          wv[j] = __ldcg(&gt.wts[s]);
+          av[j] = __ldcg(&gt.ays[s]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (k[j0 + j] != kEmptyKeyU) {
+          const int64_t s = s0 + threadIdx.x + (j0 + j) * 512;
+          gt.keys[s] = kEmptyKeyU;
+          gt.wts[s] = 0u;
+          const double g2 = modularity_gain(static_cast<double>(wv[j]), eix, vd, static_cast<double>(av[j]), ax, p.constant);
+          if (better_u(g2, k[j0 + j], g, id)) {
+            g = g2;
+            id = k[j0 + j];
+          }
         }
       }
     }
@@ -654,6 +831,219 @@ __global__ void __launch_bounds__(128) k_sweep_u32_giant_final(SweepU32Params p,
     meta[1] = 0u;
     meta[2] = 0u;
   }
+}
+
+// ---------------------------------------------------------------------------
+// First sweep of a phase (every vertex is its own community) on graphs whose
+// rows hold each tail at most once: all neighbour communities are distinct, so
+// nothing needs merging — no table, no atomics: eiy is the entry's weight and
+// the own-community weight is the self-loop.  TPV threads per vertex stride
+// over the adjacency and keep the running (gain, id) best.
+// ---------------------------------------------------------------------------
+template <int TPV>
+__global__ void __launch_bounds__(256) k_sweep_u32_first(SweepU32Params p, const vid_t *__restrict__ list, int n) {
+  constexpr int VPB = 256 / TPV;
+  constexpr int GL = TPV < 32 ? TPV : 32;
+  __shared__ double red_g[8];
+  __shared__ uint32_t red_id[8];
+  __shared__ uint32_t red_self[8];
+  const unsigned lane = threadIdx.x & 31u;
+  const int tid = static_cast<int>(threadIdx.x % TPV);
+  const int vslot = static_cast<int>(threadIdx.x / TPV);
+  // every lane of the warp stays in the loop (idle vertices are masked) so that
+  // the group reductions below run with the full-warp mask
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * VPB;
+  const int64_t first_item = static_cast<int64_t>(blockIdx.x) * VPB;
+  for (int64_t base_item = first_item; base_item < n; base_item += stride) {
+    const int64_t item = base_item + vslot;
+    const bool live = item < n;
+    const vid_t v = live ? list[item] : 0;
+    const eid_t e0 = live ? p.offsets[v] : 0, e1 = live ? p.offsets[v + 1] : 0;
+    const vid_t self = v + p.base;
+    const uint2 me = p.packed[self];
+    const double vd = p.vdeg[v];
+    // in the singleton state counter[0] == selfLoop, so eix = 0 for every gain;
+    // the self-loop weight is only needed for clusterWeight and rides along
+    const double eix = 0.0;
+    const double ax = static_cast<double>(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+    uint32_t selfw = 0u;
+    for (eid_t eb = e0 + tid; eb < e1; eb += 4 * TPV) {  // 4 independent gathers in flight per thread
+      vid_t t[4];
+      uint32_t w[4];
+      uint2 pk[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const eid_t e = eb + static_cast<eid_t>(k) * TPV;
+        t[k] = self;
+        w[k] = 0u;
+        if (e < e1) {
+          t[k] = p.tails[e];
+          w[k] = p.weights[e];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pk[k] = p.packed[t[k]];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (t[k] != self) {
+          const double g2 = modularity_gain(static_cast<double>(w[k]), eix, vd, static_cast<double>(pk[k].y), ax, p.constant);
+          if (better_u(g2, pk[k].x, g, id)) {
+            g = g2;
+            id = pk[k].x;
+          }
+        } else {
+          selfw += w[k];  // idle slots carry w = 0
+        }
+      }
+    }
+    uint32_t slu = selfw;
+    if (TPV > 1) {
+#pragma unroll
+      for (int o = GL / 2; o > 0; o >>= 1) slu += __shfl_xor_sync(0xffffffffu, slu, o);
+    }
+    if (TPV > 32) {
+      if (lane == 0) red_self[threadIdx.x >> 5] = slu;
+      __syncthreads();
+      slu = 0u;
+      for (int i = 0; i < TPV / 32; ++i) slu += red_self[i];
+    }
+    const double counter0 = static_cast<double>(slu);
+    if (TPV > 1) {
+#pragma unroll
+      for (int o = GL / 2; o > 0; o >>= 1) {
+        const double g2 = __shfl_xor_sync(0xffffffffu, g, o);
+        const uint32_t k2 = __shfl_xor_sync(0xffffffffu, id, o);
+        if (better_u(g2, k2, g, id)) {
+          g = g2;
+          id = k2;
+        }
+      }
+    }
+    if (TPV > 32) {
+      if (lane == 0) {
+        red_g[threadIdx.x >> 5] = g;
+        red_id[threadIdx.x >> 5] = id;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0)
+        for (int i = 1; i < TPV / 32; ++i)
+          if (better_u(red_g[i], red_id[i], g, id)) {
+            g = red_g[i];
+            id = red_id[i];
+          }
+    }
+    if (live && tid == 0) commit_vertex_u32(p, v, me.x, g, id, vd, counter0);
+    if (TPV > 32) __syncthreads();
+  }
+}
+
+// Giant vertices in the first sweep: 4096-entry chunks over the whole grid, one
+// (gain, key) candidate per chunk, then k_sweep_u32_first_giant_final.
+__global__ void __launch_bounds__(512) k_sweep_u32_first_giant(SweepU32Params p, const vid_t *__restrict__ list, int n,
+                                                              GiantTables gt, int64_t total_chunks,
+                                                              double *__restrict__ chunk_gain,
+                                                              uint32_t *__restrict__ chunk_key) {
+  __shared__ double red_g[16];
+  __shared__ uint32_t red_id[16];
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = threadIdx.x >> 5;
+  for (int64_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    const int gi = giant_owner(gt.chunk_start, n, chunk);
+    const vid_t v = list[gi];
+    const eid_t ve0 = p.offsets[v], ve1 = p.offsets[v + 1];
+    const eid_t e0 = ve0 + (chunk - gt.chunk_start[gi]) * kGiantChunk;
+    const eid_t e1 = (e0 + kGiantChunk < ve1) ? e0 + kGiantChunk : ve1;
+    const vid_t self = v + p.base;
+    const uint2 me = p.packed[self];
+    const double vd = p.vdeg[v];
+    const double ax = static_cast<double>(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask, selfw = 0u;
+    vid_t t[8];
+    uint32_t w[8];
+    uint2 pk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const eid_t e = e0 + threadIdx.x + static_cast<eid_t>(k) * 512;
+      t[k] = self;
+      w[k] = 0u;
+      if (e < e1) {
+        t[k] = p.tails[e];
+        w[k] = p.weights[e];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pk[k] = p.packed[t[k]];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (t[k] != self) {
+        const double g2 = modularity_gain(static_cast<double>(w[k]), 0.0, vd, static_cast<double>(pk[k].y), ax, p.constant);
+        if (better_u(g2, pk[k].x, g, id)) {
+          g = g2;
+          id = pk[k].x;
+        }
+      } else {
+        selfw += w[k];
+      }
+    }
+    const uint32_t slu = __reduce_add_sync(0xffffffffu, selfw);
+    if (lane == 0 && slu) atomicAdd(&gt.gmeta[3 * static_cast<int64_t>(gi) + 1], slu);
+    double wg;
+    uint32_t wid = warp_argmax(g, id, &wg);
+    if (lane == 0) {
+      red_g[wib] = wg;
+      red_id[wib] = wid;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < 16; ++i)
+        if (better_u(red_g[i], red_id[i], wg, wid)) {
+          wg = red_g[i];
+          wid = red_id[i];
+        }
+      chunk_gain[chunk] = wg;
+      chunk_key[chunk] = wid;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(128) k_sweep_u32_first_giant_final(SweepU32Params p, const vid_t *__restrict__ list,
+                                                                    int n, GiantTables gt,
+                                                                    const double *__restrict__ chunk_gain,
+                                                                    const uint32_t *__restrict__ chunk_key) {
+  const int gi = static_cast<int>((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+  const unsigned lane = threadIdx.x & 31u;
+  if (gi >= n) return;
+  const vid_t v = list[gi];
+  const uint2 me = p.packed[v + p.base];
+  double g = -1.0;
+  uint32_t id = kLabelMask;
+  for (int64_t q = gt.chunk_start[gi] + lane; q < gt.chunk_start[gi + 1]; q += 32)
+    if (better_u(chunk_gain[q], chunk_key[q], g, id)) {
+      g = chunk_gain[q];
+      id = chunk_key[q];
+    }
+  double wg;
+  const uint32_t wid = warp_argmax(g, id, &wg);
+  if (lane == 0) {
+    uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
+    commit_vertex_u32(p, v, me.x, wg, wid, p.vdeg[v], static_cast<double>(meta[1]));  // counter[0] = self-loop
+    meta[1] = 0u;
+  }
+}
+
+// rows_simple[0] = 0 when some row holds a tail twice or out of order
+__global__ void k_check_simple_rows(const eid_t *__restrict__ offsets, const vid_t *__restrict__ tails, int64_t nv,
+                                    int *__restrict__ not_simple) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  if (row >= nv) return;
+  int bad = 0;
+  for (eid_t e = offsets[row] + 1 + lane; e < offsets[row + 1]; e += 32) bad |= tails[e] <= tails[e - 1];
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(not_simple, 1);
 }
 
 }  // namespace cvb
