@@ -120,10 +120,13 @@ struct cvb_engine {
   // CVB_WEIGHTS_U32 fast path
   DevBuf<uint2> packed;                 // [nv_global] {label|singleton bit, community degree}
   DevBuf<int64_t> giant_layout;         // chunk_start[ng+1], table_start[ng+1]
-  DevBuf<uint32_t> gkeys, gwts, gays, gmeta, gpiece_key;
+  DevBuf<uint32_t> gmeta, gpiece_key;
+  DevBuf<uint4> gslots;
   DevBuf<double> gpiece_gain, gchunk_gain;
   DevBuf<uint32_t> gchunk_key;
+  DevBuf<int32_t> gchunk_owner;
   int64_t giant_chunks = 0, giant_slots = 0;
+  bool giant_direct = false;   // CVB_GIANT_DIRECT=1: giant entries go straight to the global tables
   bool use_first_sweep = true; // cvb env CVB_NO_FIRST_SWEEP=1 disables the singleton fast path
   bool rows_simple = false;    // every row holds each tail at most once (ascending)
   int sweeps_in_phase = 0;     // 0 right after cvb_phase_begin: all vertices are singletons
@@ -283,9 +286,10 @@ int launch_sweep_u32(cvb_engine *e) {
     go(k_sweep_u32_first<1>, 1, kClsG4, kClsG8, e->aux[3]);
     if ((n = cnt(kClsGiant)) > 0) {
       GiantTables gt;
+      gt.chunk_owner = e->gchunk_owner.p;
       gt.chunk_start = e->giant_layout.p;
       gt.table_start = e->giant_layout.p + (n + 1);
-      gt.keys = e->gkeys.p; gt.wts = e->gwts.p; gt.ays = e->gays.p; gt.gmeta = e->gmeta.p;
+      gt.slots = e->gslots.p; gt.gmeta = e->gmeta.p;
       gt.piece_gain = e->gpiece_gain.p; gt.piece_key = e->gpiece_key.p;
       int64_t g1 = e->giant_chunks < 8LL * e->num_sms ? e->giant_chunks : 8LL * e->num_sms;
       k_sweep_u32_first_giant<<<static_cast<int>(g1), 512, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt,
@@ -313,11 +317,10 @@ int launch_sweep_u32(cvb_engine *e) {
   // stream 1: giants
   if ((n = cnt(kClsGiant)) > 0) {
     GiantTables gt;
+    gt.chunk_owner = e->gchunk_owner.p;
     gt.chunk_start = e->giant_layout.p;
     gt.table_start = e->giant_layout.p + (n + 1);
-    gt.keys = e->gkeys.p;
-    gt.wts = e->gwts.p;
-    gt.ays = e->gays.p;
+    gt.slots = e->gslots.p;
     gt.gmeta = e->gmeta.p;
     gt.piece_gain = e->gpiece_gain.p;
     gt.piece_key = e->gpiece_key.p;
@@ -329,8 +332,14 @@ int launch_sweep_u32(cvb_engine *e) {
       CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_giant_insert, cudaFuncAttributeMaxDynamicSharedMemorySize, kGiantSmem));
       giant_configured = true;
     }
-    k_sweep_u32_giant_insert<<<static_cast<int>(g1), 512, kGiantSmem, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt,
+    if (e->giant_direct) {
+      int64_t g0 = e->giant_chunks < 4LL * e->num_sms ? e->giant_chunks : 4LL * e->num_sms;
+      k_sweep_u32_giant_insert_direct<<<static_cast<int>(g0), 512, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt,
                                                                                   e->giant_chunks);
+    } else {
+      k_sweep_u32_giant_insert<<<static_cast<int>(g1), 512, kGiantSmem, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt,
+                                                                                    e->giant_chunks);
+    }
     int64_t g2 = pieces < 4LL * e->num_sms ? pieces : 4LL * e->num_sms;
     k_sweep_u32_giant_eval<<<static_cast<int>(g2), 512, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt, pieces);
     k_sweep_u32_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n,
@@ -463,16 +472,17 @@ int post_graph(cvb_engine *e) {
       CVB_CUDA(cudaStreamSynchronize(st));
       e->giant_chunks = tot[0];
       e->giant_slots = tot[1];
-      CVB_TRY(e->gkeys.ensure(e->giant_slots));
-      CVB_TRY(e->gwts.ensure(e->giant_slots));
-      CVB_TRY(e->gays.ensure(e->giant_slots));
+      CVB_TRY(e->gslots.ensure(e->giant_slots));
       CVB_TRY(e->gmeta.ensure(3 * ngiant + 4));
       CVB_TRY(e->gpiece_gain.ensure(e->giant_slots / kGiantPiece + 1));
       CVB_TRY(e->gpiece_key.ensure(e->giant_slots / kGiantPiece + 1));
       CVB_TRY(e->gchunk_gain.ensure(e->giant_chunks + 1));
       CVB_TRY(e->gchunk_key.ensure(e->giant_chunks + 1));
-      CVB_CUDA(cudaMemsetAsync(e->gkeys.p, 0xFF, e->giant_slots * sizeof(uint32_t), st));
-      CVB_CUDA(cudaMemsetAsync(e->gwts.p, 0, e->giant_slots * sizeof(uint32_t), st));
+      CVB_TRY(e->gchunk_owner.ensure(e->giant_chunks + 1));
+      k_giant_chunk_owner<<<static_cast<int>(ngiant), 64, 0, st>>>(e->giant_layout.p, (int)ngiant, e->gchunk_owner.p);
+      e->launches++;
+      k_giant_init_slots<<<grid_for(e->giant_slots, 256), 256, 0, st>>>(e->gslots.p, e->giant_slots);
+      e->launches++;
       CVB_CUDA(cudaMemsetAsync(e->gmeta.p, 0, (3 * ngiant + 4) * sizeof(uint32_t), st));
     }
   }
@@ -574,6 +584,7 @@ cvb_engine *cvb_create(void *stream) {
   cvb_engine *e = new cvb_engine;
   e->device = dev;
   if (const char *s = getenv("CVB_NO_FIRST_SWEEP")) e->use_first_sweep = !(s[0] == '1');
+  if (const char *s = getenv("CVB_GIANT_DIRECT")) e->giant_direct = (s[0] == '1');
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) e->num_sms = sms;
   if (stream) {
@@ -614,9 +625,9 @@ void cvb_destroy(cvb_engine *e) {
   e->d_class_start.release(); e->d_class_entries.release();
   e->partials.release(); e->d_sums.release(); e->ticket.release(); e->d_flags.release();
   e->h_sums.release(); e->staging.release(); e->staging2.release(); e->giant.release(); e->h_stage.release();
-  e->packed.release(); e->giant_layout.release(); e->gkeys.release(); e->gwts.release(); e->gays.release();
+  e->packed.release(); e->giant_layout.release(); e->gslots.release();
   e->gmeta.release(); e->gpiece_key.release(); e->gpiece_gain.release(); e->gchunk_gain.release();
-  e->gchunk_key.release();
+  e->gchunk_key.release(); e->gchunk_owner.release();
   for (int i = 0; i < cvb_engine::kAux; ++i) {
     if (e->aux[i]) cudaStreamDestroy(e->aux[i]);
     if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);

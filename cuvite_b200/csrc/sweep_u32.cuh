@@ -428,6 +428,8 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
     log2cap = log2cap < 4 ? 4 : (log2cap > 31 - __clz(CAP) ? 31 - __clz(CAP) : log2cap);
     const uint32_t maskb = ((1u << log2cap) - 1u) << 2;
 
+    const vid_t *__restrict__ row_tails = p.tails + e0;
+    const uint32_t *__restrict__ row_weights = p.weights + e0;
     // claims of this lane: key, community degree and slot of every entry that
     // opened a new table slot (valid where the fresh bit is set)
     uint32_t ckey[K], cay[K];
@@ -441,12 +443,12 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
         uint32_t validm = 0u;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
-          const eid_t e = e0 + tid + static_cast<eid_t>(c * KC + k) * TPV;
+          const int i = tid + (c * KC + k) * TPV;  // 32-bit position inside the row
           tail[k] = self;  // a safe address for the gather of idle lanes
           w[k] = 0u;
-          if (e < e1) {
-            tail[k] = p.tails[e];
-            w[k] = p.weights[e];
+          if (i < deg) {
+            tail[k] = __ldcs(&row_tails[i]);
+            w[k] = __ldcs(&row_weights[i]);
             validm |= 1u << k;
           }
         }
@@ -553,11 +555,10 @@ constexpr int kGiantChunk = 4096;
 constexpr int kGiantPiece = 8192;  // table capacities are multiples of this
 
 struct GiantTables {
+  const int32_t *__restrict__ chunk_owner;  // [total_chunks] giant index of every chunk
   const int64_t *__restrict__ chunk_start;  // [ngiant+1] prefix of chunks per vertex
   const int64_t *__restrict__ table_start;  // [ngiant+1] prefix of table slots per vertex
-  uint32_t *__restrict__ keys;
-  uint32_t *__restrict__ wts;
-  uint32_t *__restrict__ ays;
+  uint4 *__restrict__ slots;  // {key, weight, community degree, -}: one 16-byte sector-friendly record
   uint32_t *__restrict__ gmeta;
   double *__restrict__ piece_gain;   // [total_slots / kGiantPiece]
   uint32_t *__restrict__ piece_key;  // [total_slots / kGiantPiece]
@@ -572,12 +573,24 @@ __global__ void k_giant_layout(const eid_t *__restrict__ offsets, const vid_t *_
     table_start[i] = s;
     const int64_t deg = offsets[list[i] + 1] - offsets[list[i]];
     c += (deg + kGiantChunk - 1) / kGiantChunk;
-    int64_t cap = 16384;
-    while (cap < 2 * deg) cap <<= 1;
+    int64_t cap = kGiantPiece;
+    while (2 * cap < 3 * deg) cap <<= 1;  // load factor <= 2/3 (double hashing)
     s += cap;
   }
   chunk_start[n] = c;
   table_start[n] = s;
+}
+
+__global__ void k_giant_init_slots(uint4 *__restrict__ slots, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    slots[i] = make_uint4(kEmptyKeyU, 0u, 0u, 0u);
+}
+
+__global__ void k_giant_chunk_owner(const int64_t *__restrict__ chunk_start, int n, int32_t *__restrict__ owner) {
+  const int gi = blockIdx.x;
+  if (gi >= n) return;
+  for (int64_t c = chunk_start[gi] + threadIdx.x; c < chunk_start[gi + 1]; c += blockDim.x) owner[c] = gi;
 }
 
 __device__ __forceinline__ int giant_owner(const int64_t *__restrict__ start, int n, int64_t x) {
@@ -592,8 +605,7 @@ __device__ __forceinline__ int giant_owner(const int64_t *__restrict__ start, in
 // Global-table twin of table_insert_chunk: K independent L2 atomics in flight,
 // collided entries retry in their own short loops.
 template <int K>
-__device__ __forceinline__ void gtable_insert_chunk(uint32_t *__restrict__ keys, uint32_t *__restrict__ wts,
-                                                    uint32_t *__restrict__ ays, const uint32_t (&key)[K],
+__device__ __forceinline__ void gtable_insert_chunk(uint4 *__restrict__ slots, const uint32_t (&key)[K],
                                                     const uint32_t (&ay)[K], const uint32_t (&w)[K], uint32_t active,
                                                     int log2cap, uint32_t mask) {
   uint32_t old[K], sl[K];
@@ -602,7 +614,7 @@ __device__ __forceinline__ void gtable_insert_chunk(uint32_t *__restrict__ keys,
   for (int k = 0; k < K; ++k) {
     sl[k] = hash_key(key[k], log2cap);
     old[k] = key[k];
-    if (active & (1u << k)) old[k] = atomicCAS(&keys[sl[k]], kEmptyKeyU, key[k]);
+    if (active & (1u << k)) old[k] = atomicCAS(&slots[sl[k]].x, kEmptyKeyU, key[k]);
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -617,7 +629,7 @@ __device__ __forceinline__ void gtable_insert_chunk(uint32_t *__restrict__ keys,
     for (int k = 0; k < K; ++k)
       if (pend & (1u << k)) {
         sl[k] = (sl[k] + hash_step(key[k], log2cap)) & mask;
-        old[k] = atomicCAS(&keys[sl[k]], kEmptyKeyU, key[k]);
+        old[k] = atomicCAS(&slots[sl[k]].x, kEmptyKeyU, key[k]);
       }
 #pragma unroll
     for (int k = 0; k < K; ++k)
@@ -633,8 +645,8 @@ __device__ __forceinline__ void gtable_insert_chunk(uint32_t *__restrict__ keys,
 #pragma unroll
   for (int k = 0; k < K; ++k)
     if (active & (1u << k)) {
-      atomicAdd(&wts[sl[k]], w[k]);
-      if (fresh & (1u << k)) ays[sl[k]] = ay[k];
+      atomicAdd(&slots[sl[k]].y, w[k]);
+      if (fresh & (1u << k)) slots[sl[k]].z = ay[k];
     }
 }
 
@@ -661,7 +673,7 @@ __global__ void __launch_bounds__(512, 2) k_sweep_u32_giant_insert(SweepU32Param
   constexpr int log2cap_s = 13;  // CAP = 8192
   constexpr uint32_t maskb = (CAP - 1u) << 2;
   for (int64_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
-    const int gi = giant_owner(gt.chunk_start, n, chunk);
+    const int gi = gt.chunk_owner[chunk];
     const vid_t v = list[gi];
     const eid_t ve0 = p.offsets[v], ve1 = p.offsets[v + 1];
     const eid_t e0 = ve0 + (chunk - gt.chunk_start[gi]) * kGiantChunk;
@@ -688,8 +700,8 @@ __global__ void __launch_bounds__(512, 2) k_sweep_u32_giant_insert(SweepU32Param
         tail[k] = self;
         w[k] = 0u;
         if (e < e1) {
-          tail[k] = p.tails[e];
-          w[k] = p.weights[e];
+          tail[k] = __ldcs(&p.tails[e]);
+          w[k] = __ldcs(&p.weights[e]);
           validm |= 1u << k;
         }
       }
@@ -732,8 +744,66 @@ __global__ void __launch_bounds__(512, 2) k_sweep_u32_giant_insert(SweepU32Param
         sts_u32(a + capb, 0u);
       }
     }
-    gtable_insert_chunk<K>(gt.keys + tbase, gt.wts + tbase, gt.ays + tbase, ckey, cay, tot, freshmask, glog2, gmask);
+    gtable_insert_chunk<K>(gt.slots + tbase, ckey, cay, tot, freshmask, glog2, gmask);
     __syncthreads();
+  }
+}
+
+// Variant without the shared-memory stage: every entry goes straight to the
+// vertex's global table, 8 independent L2 atomics in flight per thread, 4 blocks
+// per SM.  (A/B against k_sweep_u32_giant_insert: CVB_GIANT_DIRECT=1.)
+__global__ void __launch_bounds__(512, 4) k_sweep_u32_giant_insert_direct(SweepU32Params p,
+                                                                         const vid_t *__restrict__ list, int n,
+                                                                         GiantTables gt, int64_t total_chunks) {
+  constexpr int K = kGiantChunk / 512;
+  const unsigned lane = threadIdx.x & 31u;
+  for (int64_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    const int gi = gt.chunk_owner[chunk];
+    const vid_t v = list[gi];
+    const eid_t ve0 = p.offsets[v], ve1 = p.offsets[v + 1];
+    const eid_t e0 = ve0 + (chunk - gt.chunk_start[gi]) * kGiantChunk;
+    const int cnt = static_cast<int>(((e0 + kGiantChunk < ve1) ? e0 + kGiantChunk : ve1) - e0);
+    const vid_t self = v + p.base;
+    const uint32_t cc = p.packed[self].x & kLabelMask;
+    const int64_t tbase = gt.table_start[gi];
+    const int64_t gcap = gt.table_start[gi + 1] - tbase;
+    const int glog2 = 63 - __clzll(gcap);
+    const uint32_t gmask = static_cast<uint32_t>(gcap - 1);
+    uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
+    const vid_t *__restrict__ row_tails = p.tails + e0;
+    const uint32_t *__restrict__ row_weights = p.weights + e0;
+    uint32_t key[K], ay[K], w[K];
+    vid_t tail[K];
+    uint32_t validm = 0u, active = 0u, ownsum = 0u, selfsum = 0u;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int i = threadIdx.x + k * 512;
+      tail[k] = self;
+      w[k] = 0u;
+      if (i < cnt) {
+        tail[k] = __ldcs(&row_tails[i]);
+        w[k] = __ldcs(&row_weights[i]);
+        validm |= 1u << k;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const uint2 pk = p.packed[tail[k]];
+      const bool valid = (validm >> k) & 1u;
+      key[k] = valid ? pk.x : kEmptyKeyU;
+      ay[k] = pk.y;
+      const bool own = (key[k] & kLabelMask) == cc;
+      ownsum += own ? w[k] : 0u;
+      selfsum += (valid && tail[k] == self) ? w[k] : 0u;
+      active |= (valid && !own) ? (1u << k) : 0u;
+    }
+    gtable_insert_chunk<K>(gt.slots + tbase, key, ay, w, active, glog2, gmask);
+    const uint32_t c0u = __reduce_add_sync(0xffffffffu, ownsum);
+    const uint32_t slu = __reduce_add_sync(0xffffffffu, selfsum);
+    if (lane == 0) {
+      if (c0u) atomicAdd(&meta[2], c0u);
+      if (slu) atomicAdd(&meta[1], slu);
+    }
   }
 }
 
@@ -755,32 +825,19 @@ __global__ void __launch_bounds__(512) k_sweep_u32_giant_eval(SweepU32Params p, 
     const double ax = static_cast<double>(me.y) - vd;
     double g = -1.0;
     uint32_t id = kLabelMask;
-    uint32_t k[kGiantPiece / 512];
 #pragma unroll
-    for (int j = 0; j < kGiantPiece / 512; ++j) k[j] = __ldcg(&gt.keys[s0 + threadIdx.x + j * 512]);
+    for (int j0 = 0; j0 < kGiantPiece / 512; j0 += 4) {  // four 16-byte records in flight per thread
+      uint4 r[4];
 #pragma unroll
-    for (int j0 = 0; j0 < kGiantPiece / 512; j0 += 4) {  // 4 slots' dependent loads in flight together
-      uint32_t wv[4], av[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        wv[j] = 0u;
-        av[j] = 0u;
-        if (k[j0 + j] != kEmptyKeyU) {
-          const int64_t s = s0 + threadIdx.x + (j0 + j) * 512;
-          wv[j] = __ldcg(&gt.wts[s]);
-          av[j] = __ldcg(&gt.ays[s]);
-        }
-      }
+      for (int j = 0; j < 4; ++j) r[j] = __ldcg(&gt.slots[s0 + threadIdx.x + (j0 + j) * 512]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (k[j0 + j] != kEmptyKeyU) {
-          const int64_t s = s0 + threadIdx.x + (j0 + j) * 512;
-          gt.keys[s] = kEmptyKeyU;
-          gt.wts[s] = 0u;
-          const double g2 = modularity_gain(static_cast<double>(wv[j]), eix, vd, static_cast<double>(av[j]), ax, p.constant);
-          if (better_u(g2, k[j0 + j], g, id)) {
+        if (r[j].x != kEmptyKeyU) {
+          gt.slots[s0 + threadIdx.x + (j0 + j) * 512] = make_uint4(kEmptyKeyU, 0u, 0u, 0u);
+          const double g2 = modularity_gain(static_cast<double>(r[j].y), eix, vd, static_cast<double>(r[j].z), ax, p.constant);
+          if (better_u(g2, r[j].x, g, id)) {
             g = g2;
-            id = k[j0 + j];
+            id = r[j].x;
           }
         }
       }
@@ -879,8 +936,8 @@ __global__ void __launch_bounds__(256) k_sweep_u32_first(SweepU32Params p, const
         t[k] = self;
         w[k] = 0u;
         if (e < e1) {
-          t[k] = p.tails[e];
-          w[k] = p.weights[e];
+          t[k] = __ldcs(&p.tails[e]);
+          w[k] = __ldcs(&p.weights[e]);
         }
       }
 #pragma unroll
@@ -950,7 +1007,7 @@ __global__ void __launch_bounds__(512) k_sweep_u32_first_giant(SweepU32Params p,
   const unsigned lane = threadIdx.x & 31u;
   const int wib = threadIdx.x >> 5;
   for (int64_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
-    const int gi = giant_owner(gt.chunk_start, n, chunk);
+    const int gi = gt.chunk_owner[chunk];
     const vid_t v = list[gi];
     const eid_t ve0 = p.offsets[v], ve1 = p.offsets[v + 1];
     const eid_t e0 = ve0 + (chunk - gt.chunk_start[gi]) * kGiantChunk;
@@ -970,8 +1027,8 @@ __global__ void __launch_bounds__(512) k_sweep_u32_first_giant(SweepU32Params p,
       t[k] = self;
       w[k] = 0u;
       if (e < e1) {
-        t[k] = p.tails[e];
-        w[k] = p.weights[e];
+        t[k] = __ldcs(&p.tails[e]);
+        w[k] = __ldcs(&p.weights[e]);
       }
     }
 #pragma unroll
