@@ -36,6 +36,7 @@ SIGNATURES = {
     "cvb_phase_begin": (_i32, [_vp, _f64]),
     "cvb_sweep": (_i32, [_vp]),
     "cvb_apply_and_reduce": (_i32, [_vp, C.POINTER(_f64)]),
+    "cvb_rebuild_and_reduce": (_i32, [_vp, C.POINTER(_f64)]),
     "cvb_modularity_from_sums": (_f64, [_vp, C.POINTER(_f64)]),
     "cvb_rotate_labels": (_i32, [_vp]),
     "cvb_phase_run": (_i32, [_vp, _f64, _f64, _i32, C.POINTER(_f64), C.POINTER(_i32)]),

@@ -90,7 +90,10 @@ struct cvb_engine {
   DevBuf<unsigned char> weights;
   DevBuf<double> vdeg, cdeg, ddeg, cw;
   DevBuf<int32_t> csize, dsize;
-  DevBuf<vid_t> lab[3], labels_global;
+  DevBuf<vid_t> lab[3], labels_global, labels_global2;  // labels_global2: gather target of the next labels
+  DevBuf<double> vdeg_global;                           // replicated vertex degrees (N > 1)
+  bool glabels_swapped = false;
+  bool labels_only = false;  // N > 1: community info rebuilt from gathered labels (cvb_rebuild_and_reduce)
   int past = 0, curr = 1, targ = 2;
   DevBuf<vid_t> list;
   DevBuf<int32_t> block_counts;
@@ -138,7 +141,11 @@ struct cvb_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool sweep_timed = false;
 
-  const vid_t *sweep_labels() const { return nvl == nvg ? lab[curr].p : labels_global.p; }
+  vid_t *glabels_curr() { return glabels_swapped ? labels_global2.p : labels_global.p; }
+  vid_t *glabels_next() { return glabels_swapped ? labels_global.p : labels_global2.p; }
+  const vid_t *sweep_labels() const {
+    return nvl == nvg ? lab[curr].p : (glabels_swapped ? labels_global2.p : labels_global.p);
+  }
 };
 
 namespace {
@@ -187,8 +194,8 @@ int launch_sweep(cvb_engine *e) {
   p.base = static_cast<vid_t>(e->base);
   p.target = e->lab[e->targ].p;
   p.cw = e->cw.p;
-  p.ddeg = e->ddeg.p;
-  p.dsize = e->dsize.p;
+  p.ddeg = e->labels_only ? nullptr : e->ddeg.p;
+  p.dsize = e->labels_only ? nullptr : e->dsize.p;
   auto cnt = [&](int c) { return e->class_start[c + 1] - e->class_start[c]; };
   auto lst = [&](int c) { return e->list.p + e->class_start[c]; };
   int64_t n;
@@ -260,8 +267,8 @@ int launch_sweep_u32(cvb_engine *e) {
   p.base = static_cast<vid_t>(e->base);
   p.target = e->lab[e->targ].p;
   p.cw = e->cw.p;
-  p.ddeg = e->ddeg.p;
-  p.dsize = e->dsize.p;
+  p.ddeg = e->labels_only ? nullptr : e->ddeg.p;  // labels-only exchange derives the deltas from labels
+  p.dsize = e->labels_only ? nullptr : e->dsize.p;
   auto cnt = [&](int c) { return e->class_start[c + 1] - e->class_start[c]; };
   auto lst = [&](int c) { return e->list.p + e->class_start[c]; };
   int64_t n;
@@ -396,7 +403,11 @@ int post_graph(cvb_engine *e) {
   CVB_TRY(e->ddeg.ensure(e->nvg + 1));
   CVB_TRY(e->csize.ensure(e->nvg + 1));
   CVB_TRY(e->dsize.ensure(e->nvg + 1));
-  if (e->nvl != e->nvg) CVB_TRY(e->labels_global.ensure(e->nvg + 1));
+  if (e->nvl != e->nvg) {
+    CVB_TRY(e->labels_global.ensure(e->nvg + 1));
+    CVB_TRY(e->labels_global2.ensure(e->nvg + 1));
+    CVB_TRY(e->vdeg_global.ensure(e->nvg + 1));
+  }
   if (nvl > 0) {
     if (e->mode == CVB_WEIGHTS_U32)
       k_vertex_degree<uint32_t><<<static_cast<int>((nvl * 32 + 255) / 256), 256, 0, st>>>(
@@ -621,7 +632,7 @@ void cvb_destroy(cvb_engine *e) {
   e->vdeg.release(); e->cdeg.release(); e->ddeg.release(); e->cw.release();
   e->csize.release(); e->dsize.release();
   for (auto &l : e->lab) l.release();
-  e->labels_global.release(); e->list.release(); e->block_counts.release();
+  e->labels_global.release(); e->labels_global2.release(); e->vdeg_global.release(); e->list.release(); e->block_counts.release();
   e->d_class_start.release(); e->d_class_entries.release();
   e->partials.release(); e->d_sums.release(); e->ticket.release(); e->d_flags.release();
   e->h_sums.release(); e->staging.release(); e->staging2.release(); e->giant.release(); e->h_stage.release();
@@ -705,6 +716,8 @@ int cvb_phase_begin(cvb_engine *e, double total_weight) {
   const double tot = total_weight > 0.0 ? total_weight : e->local_weight;
   e->constant = 1.0 / tot;  // louvain.cpp:2182
   e->past = 0; e->curr = 1; e->targ = 2;
+  e->glabels_swapped = false;
+  e->labels_only = false;
   cudaStream_t st = e->stream;
   if (e->nvl > 0) {
     k_phase_init_local<<<grid_for(e->nvl, 256), 256, 0, st>>>(e->nvl, static_cast<vid_t>(e->base), e->lab[0].p,
@@ -717,9 +730,12 @@ int cvb_phase_begin(cvb_engine *e, double total_weight) {
                                                               single ? nullptr : e->labels_global.p, e->cdeg.p,
                                                               e->csize.p, e->ddeg.p, e->dsize.p);
     e->launches++;
-    if (!single && e->nvl > 0)
+    if (!single && e->nvl > 0) {
       CVB_CUDA(cudaMemcpyAsync(e->cdeg.p + e->base, e->vdeg.p, e->nvl * sizeof(double), cudaMemcpyDeviceToDevice,
                                st));
+      CVB_CUDA(cudaMemcpyAsync(e->vdeg_global.p + e->base, e->vdeg.p, e->nvl * sizeof(double),
+                               cudaMemcpyDeviceToDevice, st));
+    }
   }
   CVB_CUDA(cudaGetLastError());
   e->phase_ready = true;
@@ -755,6 +771,17 @@ static int apply_reduce_async(cvb_engine *e) {
   return CVB_OK;
 }
 
+// labels-only mode: Cinfo was rebuilt from labels; only zero the local deltas and reduce
+static int apply_reduce_zero_deltas(cvb_engine *e) {
+  cudaStream_t st = e->stream;
+  if (!e->labels_only) {  // first use in this phase: the first sweep still wrote deltas
+    CVB_CUDA(cudaMemsetAsync(e->ddeg.p, 0, e->nvg * sizeof(double), st));
+    CVB_CUDA(cudaMemsetAsync(e->dsize.p, 0, e->nvg * sizeof(int32_t), st));
+    e->labels_only = true;
+  }
+  return apply_reduce_async(e);
+}
+
 int cvb_apply_and_reduce(cvb_engine *e, double sums[2]) {
   CVB_CHECK(e && e->phase_ready && sums, CVB_ERR_STATE, "cvb_apply_and_reduce: no phase");
   CVB_TRY(apply_reduce_async(e));
@@ -768,8 +795,23 @@ double cvb_modularity_from_sums(const cvb_engine *e, const double sums[2]) {
   return (sums[0] * c) - (sums[1] * c * c);  // louvain.cpp:2472-2473
 }
 
+int cvb_rebuild_and_reduce(cvb_engine *e, double sums[2]) {
+  CVB_CHECK(e && e->phase_ready && sums, CVB_ERR_STATE, "cvb_rebuild_and_reduce: no phase");
+  CVB_CHECK(e->nvl != e->nvg, CVB_ERR_STATE, "cvb_rebuild_and_reduce is the N > 1 path");
+  cudaStream_t st = e->stream;
+  k_apply_label_diff<<<grid_for(e->nvg, 256), 256, 0, st>>>(e->nvg, e->glabels_curr(), e->glabels_next(),
+                                                            e->vdeg_global.p, e->cdeg.p, e->csize.p);
+  e->launches++;
+  // the sweep's own delta arrays are not used in this mode (kernels skip them once labels_only is set)
+  CVB_TRY(apply_reduce_zero_deltas(e));
+  CVB_CUDA(cudaStreamSynchronize(st));
+  memcpy(sums, e->h_sums.p, 2 * sizeof(double));
+  return CVB_OK;
+}
+
 int cvb_rotate_labels(cvb_engine *e) {
   CVB_CHECK(e && e->phase_ready, CVB_ERR_STATE, "no phase");
+  if (e->nvl != e->nvg && e->labels_only) e->glabels_swapped = !e->glabels_swapped;
   const int oldpast = e->past;  // louvain.cpp:562-567
   e->past = e->curr;
   e->curr = e->targ;
@@ -842,6 +884,8 @@ void *cvb_buffer(cvb_engine *e, int which) {
   if (!e) return nullptr;
   switch (which) {
     case CVB_BUF_LABELS_GLOBAL: return const_cast<vid_t *>(e->sweep_labels());
+    case CVB_BUF_LABELS_GLOBAL_NEXT: return e->nvl == e->nvg ? e->lab[e->targ].p : e->glabels_next();
+    case CVB_BUF_VDEG_GLOBAL: return e->nvl == e->nvg ? e->vdeg.p : e->vdeg_global.p;
     case CVB_BUF_LABELS_CURR: return e->lab[e->curr].p;
     case CVB_BUF_LABELS_TARGET: return e->lab[e->targ].p;
     case CVB_BUF_LABELS_PAST: return e->lab[e->past].p;

@@ -343,6 +343,28 @@ __global__ void __launch_bounds__(kReduceBlock) k_apply_reduce(int64_t nv_global
   }
 }
 
+// ---- labels-only exchange (N > 1) ------------------------------------------------
+// Every rank holds the replicated labels before (curr) and after (next) the
+// sweep, so it derives the community deltas of ALL ranks' moves locally:
+// cdeg[next] += vdeg, cdeg[curr] -= vdeg, sizes +-1 for every vertex that moved.
+// Exact for integer degrees; work and atomic traffic are proportional to the
+// number of moved vertices, and nothing but the labels crossed NVLink.
+__global__ void k_apply_label_diff(int64_t nv_global, const vid_t *__restrict__ curr, const vid_t *__restrict__ next,
+                                   const double *__restrict__ vdeg_global, double *__restrict__ cdeg,
+                                   int32_t *__restrict__ csize) {
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < nv_global;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const vid_t a = curr[v], b = next[v];
+    if (a != b) {
+      const double d = vdeg_global[v];
+      atomicAdd(&cdeg[b], d);
+      atomicAdd(&cdeg[a], -d);
+      atomicAdd(&csize[b], 1);
+      atomicAdd(&csize[a], -1);
+    }
+  }
+}
+
 // ---- boundary-call helpers ---------------------------------------------------
 __global__ void k_scatter_labels(int64_t n, const int64_t *__restrict__ idx, const int64_t *__restrict__ val,
                                  vid_t *__restrict__ dst) {

@@ -77,7 +77,7 @@ __device__ __forceinline__ void commit_vertex(const SweepParams &p, vid_t v, vid
   }
   p.target[v] = best;
   p.cw[v] = counter0;
-  if (best != cc) {
+  if (best != cc && p.ddeg != nullptr) {  // nullptr: labels-only exchange derives the deltas from labels
     atomicAdd(&p.ddeg[best], vd);
     atomicAdd(&p.dsize[best], 1);
     atomicAdd(&p.ddeg[cc], -vd);

@@ -71,7 +71,7 @@ __device__ __forceinline__ void commit_vertex_u32(const SweepU32Params &p, vid_t
   if (best != cc && best > cc && (best_key & kSingletonBit) && (me_key & kSingletonBit)) best = cc;
   p.target[v] = best;
   p.cw[v] = counter0;
-  if (best != cc) {
+  if (best != cc && p.ddeg != nullptr) {
     atomicAdd(&p.ddeg[best], vd);
     atomicAdd(&p.dsize[best], 1);
     atomicAdd(&p.ddeg[cc], -vd);

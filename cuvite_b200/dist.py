@@ -6,13 +6,17 @@ the Allreduce of distComputeModularity 2466/2522 and of
 distCalcConstantForSecondTerm 2175) with collectives over NVLink, keeping the
 reference's partition ``parts[p] = nv*p // P`` (distgraph.cpp:118-119).
 
-Per sweep, on every rank:
-  1. local sweep kernels read the replicated label / community arrays and add
-     their moves into global-size delta arrays;
-  2. ``all_reduce(SUM)`` of the degree / size deltas  (replaces the Cupdate push);
-  3. apply + reduce on device, ``all_reduce(SUM)`` of the two modularity sums;
-  4. rotate labels; ``all_gather`` of the new local labels into the replicated
-     label array (replaces the ghost-label pull; no request/reply round at all).
+Per sweep, on every rank (default "labels-only" exchange):
+  1. local sweep kernels read the replicated label / community arrays;
+  2. ONE ``all_gather`` of the new local labels (4 bytes per vertex) into the
+     "next" replicated label array — replaces the ghost-label pull;
+  3. every rank rebuilds the replicated community info from those labels and the
+     replicated vertex degrees on its own GPU (``cvb_rebuild_and_reduce``) — the
+     Cupdate push and the remote-community request/reply are gone, not just
+     re-expressed; ``all_reduce(SUM)`` of the two modularity sums;
+  4. accept: rotate, which swaps the two replicated label arrays.
+(``exchange="deltas"`` keeps the first version: dense ``all_reduce`` of the
+per-sweep degree/size deltas + label all-gather after the rotation.)
 With integer weights every sum is exact, so an N-GPU phase is bit-identical to
 the 1-GPU phase (tests/test_dist_gloo.py checks the orchestration on CPU with a
 stand-in local engine; tests/test_gpu_parity.py checks it on GPUs).
@@ -46,8 +50,10 @@ def tensor_of(engine, name: str) -> torch.Tensor:
 class DistLouvain:
     """One phase of distributed Louvain over ``world`` vertex-range partitions."""
 
-    def __init__(self, engine, rank: int, world: int, nv_global: int, group=None):
+    def __init__(self, engine, rank: int, world: int, nv_global: int, group=None, exchange: str = "labels"):
         self.e, self.rank, self.world, self.nvg, self.group = engine, rank, world, nv_global, group
+        assert exchange in ("labels", "deltas")
+        self.labels_only = exchange == "labels"
         self.parts = partition_ranges(nv_global, world)
         self.base, self.bound = self.parts[rank], self.parts[rank + 1]
         self.even = len({self.parts[p + 1] - self.parts[p] for p in range(world)}) == 1
@@ -84,15 +90,21 @@ class DistLouvain:
         self.constant = 1.0 / self.total_weight
         if self.world > 1:
             self._all_gather_rows(tensor_of(e, "cdeg"), tensor_of(e, "vdeg"))
+            if self.labels_only:
+                tensor_of(e, "vdeg_global").copy_(tensor_of(e, "cdeg"))
 
     def sweep(self):
         """One synchronous sweep + exchange.  Returns the modularity of this iteration."""
         e = self.e
         e.sweep()
-        if self.world > 1:
-            self._all_reduce(tensor_of(e, "ddeg"))
-            self._all_reduce(tensor_of(e, "dsize"))
-        sums = e.apply_and_reduce()
+        if self.world > 1 and self.labels_only:
+            self._all_gather_rows(tensor_of(e, "labels_global_next"), tensor_of(e, "labels_target"))
+            sums = e.rebuild_and_reduce()
+        else:
+            if self.world > 1:
+                self._all_reduce(tensor_of(e, "ddeg"))
+                self._all_reduce(tensor_of(e, "dsize"))
+            sums = e.apply_and_reduce()
         if self.world > 1:
             s = torch.tensor(sums, dtype=torch.float64, device=self.dev)
             self._all_reduce(s)
@@ -103,8 +115,8 @@ class DistLouvain:
     def advance(self):
         """Accept the sweep: rotate (louvain.cpp:562-567) and publish the new labels."""
         e = self.e
-        e.rotate_labels()
-        if self.world > 1:
+        e.rotate_labels()  # labels-only mode: also swaps the two replicated label arrays
+        if self.world > 1 and not self.labels_only:
             self._all_gather_rows(tensor_of(e, "labels_global"), tensor_of(e, "labels_curr"))
 
     def run_phase(self, lower: float = -1.0, thresh: float = 1e-6, max_iters: int = 0):

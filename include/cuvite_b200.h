@@ -119,6 +119,16 @@ int cvb_sweep(cvb_engine *e);
  * ([base, base+nv_local)).  Synchronises the stream; sums is a HOST pointer. */
 int cvb_apply_and_reduce(cvb_engine *e, double sums[2]);
 
+/* N > 1, labels-only exchange.  After the sweep the ranks all-gather their
+ * target labels into CVB_BUF_LABELS_GLOBAL_NEXT; this call then REBUILDS the
+ * replicated community info from those labels and the replicated vertex
+ * degrees (CVB_BUF_VDEG_GLOBAL) instead of reducing per-sweep deltas across
+ * ranks — it replaces updateRemoteCommunities (louvain.cpp:2983-3116) and the
+ * remote half of fillRemoteCommunities (2696-2954) with zero bytes on the wire —
+ * and returns the same two sums as cvb_apply_and_reduce.  cvb_rotate_labels
+ * then also swaps the two global label arrays. */
+int cvb_rebuild_and_reduce(cvb_engine *e, double sums[2]);
+
 /* Q = e*c - a2*c*c (louvain.cpp:2472-2473) from globally reduced sums. */
 double cvb_modularity_from_sums(const cvb_engine *e, const double sums[2]);
 
@@ -157,7 +167,9 @@ enum {
   CVB_BUF_CW = 9,            /* double[nv_local]  clusterWeight                     */
   CVB_BUF_OFFSETS = 10,      /* int64[nv_local+1]                                   */
   CVB_BUF_TAILS = 11,        /* int32[ne_local]                                     */
-  CVB_BUF_WEIGHTS = 12       /* uint32 or double [ne_local], see weight_mode        */
+  CVB_BUF_WEIGHTS = 12,      /* uint32 or double [ne_local], see weight_mode        */
+  CVB_BUF_LABELS_GLOBAL_NEXT = 13, /* int32[nv_global] gather target for the NEXT labels (N>1) */
+  CVB_BUF_VDEG_GLOBAL = 14   /* double[nv_global] every vertex's degree (N>1, replicated)   */
 };
 void *cvb_buffer(cvb_engine *e, int which);
 void *cvb_stream(cvb_engine *e);

@@ -21,7 +21,7 @@ def main():
     stream = torch.cuda.Stream()
     ok = True
     with torch.cuda.stream(stream):
-        for name in ("rmat10_intw", "hub30k", "er1k"):
+        for name, exchange in (("rmat10_intw", "labels"), ("hub30k", "labels"), ("er1k", "labels"), ("hub30k", "deltas")):
             g = np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz"))
             o, t, w = g["offsets"], g["tails"].astype(np.int64), g["weights"]
             nv = o.size - 1
@@ -29,9 +29,9 @@ def main():
             b0, b1 = parts[rank], parts[rank + 1]
             gpu = GpuGraph(stream=stream.cuda_stream)
             gpu.upload(o[b0:b1 + 1] - o[b0], t[o[b0]:o[b1]], w[o[b0]:o[b1]], base=b0, nv_global=nv)
-            q, iters = DistLouvain(gpu, rank, world, nv).run_phase()
+            q, iters = DistLouvain(gpu, rank, world, nv, exchange=exchange).run_phase()
             good = iters == int(g["iters"]) and q == float(g["q"]) and np.array_equal(gpu.labels(0), g["cvect"][b0:b1])
-            print(f"rank {rank} {name}: q={q!r} iters={iters} ok={good}", flush=True)
+            print(f"rank {rank} {name} [{exchange}]: q={q!r} iters={iters} ok={good}", flush=True)
             ok &= bool(good)
             gpu.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")

@@ -30,6 +30,9 @@ class OracleEngine:
                   "ddeg": torch.zeros(self.nvg, dtype=torch.float64), "dsize": torch.zeros(self.nvg, dtype=torch.int64),
                   "vdeg": torch.from_numpy(self.vdeg)}
         self.T["cdeg"][self.base:self.base + self.nvl] = self.T["vdeg"]
+        self.T["vdeg_global"] = torch.zeros(self.nvg, dtype=torch.float64)
+        self.T["labels_global_next"] = torch.arange(self.nvg, dtype=torch.int64)
+        self.labels_only = False
         ids = torch.arange(self.base, self.base + self.nvl, dtype=torch.int64)
         self.lab = [ids.clone(), ids.clone(), ids.clone()]
         self.past, self.curr, self.targ = 0, 1, 2
@@ -38,6 +41,8 @@ class OracleEngine:
     def tensor(self, name):
         if name == "labels_curr":
             return self.lab[self.curr]
+        if name == "labels_target":
+            return self.lab[self.targ]
         if name == "labels_past":
             return self.lab[self.past]
         if name == "labels_global" and self.nvl == self.nvg:
@@ -61,8 +66,21 @@ class OracleEngine:
         own = self.T["cdeg"][self.base:self.base + self.nvl].numpy()
         return np.array([self.cw.sum(), (own * own).sum()])
 
+    def rebuild_and_reduce(self):
+        """cvb_rebuild_and_reduce: community info from the gathered next labels."""
+        self.labels_only = True
+        nxt = self.T["labels_global_next"]
+        self.T["cdeg"].zero_().index_add_(0, nxt, self.T["vdeg_global"])
+        self.T["csize"].zero_().index_add_(0, nxt, torch.ones(self.nvg, dtype=torch.int64))
+        self.T["ddeg"].zero_()
+        self.T["dsize"].zero_()
+        own = self.T["cdeg"][self.base:self.base + self.nvl].numpy()
+        return np.array([self.cw.sum(), (own * own).sum()])
+
     def rotate_labels(self):
         self.past, self.curr, self.targ = self.curr, self.targ, self.past
+        if self.labels_only:
+            self.T["labels_global"], self.T["labels_global_next"] = self.T["labels_global_next"], self.T["labels_global"]
 
     def last_sweep_ms(self):
         return 0.0

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, name, ret):
+def _worker(rank, world, port, name, exchange, ret):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -31,7 +31,7 @@ def _worker(rank, world, port, name, ret):
     orc = Oracle()
     orc.set_num_threads(1)
     eng = OracleEngine(orc).upload(o[b0:b1 + 1] - o[b0], t[o[b0]:o[b1]], w[o[b0]:o[b1]], base=b0, nv_global=nv)
-    dl = DistLouvain(eng, rank, world, nv)
+    dl = DistLouvain(eng, rank, world, nv, exchange=exchange)
     q, iters = dl.run_phase()
     past = eng.tensor("labels_past").numpy()
     ok = (iters == int(g["iters"]) and abs(q - float(g["q"])) < 1e-12 and np.array_equal(past, g["cvect"][b0:b1]))
@@ -40,12 +40,13 @@ def _worker(rank, world, port, name, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,name", [(2, "rmat10_intw"), (3, "er1k"), (2, "hub30k")])
-def test_distributed_phase_equals_one_rank_reference(oracle, world, name):
-    port = 29600 + world * 7 + len(name)
+@pytest.mark.parametrize("world,name,exchange", [(2, "rmat10_intw", "labels"), (3, "er1k", "labels"),
+                                                 (2, "hub30k", "labels"), (3, "rmat10_intw", "deltas")])
+def test_distributed_phase_equals_one_rank_reference(oracle, world, name, exchange):
+    port = 29600 + world * 7 + len(name) + (50 if exchange == "deltas" else 0)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, name, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, name, exchange, ret), nprocs=world, join=True)
     assert len(ret) == world
     for r in range(world):
         assert ret[r][0], f"rank {r}: {ret[r]}"
