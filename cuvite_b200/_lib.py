@@ -18,7 +18,7 @@ _vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_double
 class GraphInfo(C.Structure):
     _fields_ = [("nv_local", _i64), ("base", _i64), ("nv_global", _i64), ("ne_local", _i64),
                 ("weight_mode", C.c_int32), ("num_classes", C.c_int32),
-                ("class_count", _i64 * 16), ("class_entries", _i64 * 16),
+                ("class_count", _i64 * 24), ("class_entries", _i64 * 24),
                 ("max_degree", _i64), ("local_weight", _f64)]
 
 
@@ -37,6 +37,7 @@ SIGNATURES = {
     "cvb_sweep": (_i32, [_vp]),
     "cvb_apply_and_reduce": (_i32, [_vp, C.POINTER(_f64)]),
     "cvb_rebuild_and_reduce": (_i32, [_vp, C.POINTER(_f64)]),
+    "cvb_rebuild_and_reduce_async": (_i32, [_vp]),
     "cvb_modularity_from_sums": (_f64, [_vp, C.POINTER(_f64)]),
     "cvb_rotate_labels": (_i32, [_vp]),
     "cvb_phase_run": (_i32, [_vp, _f64, _f64, _i32, C.POINTER(_f64), C.POINTER(_i32)]),

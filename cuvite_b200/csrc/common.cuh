@@ -60,8 +60,11 @@ enum : int {
   kClsH4K = 10,  // 1025..2048
   kClsH8K = 11,  // 2049..4096
   kClsH16K = 12, // 4097..8192
-  kClsGiant = 13,  // > 8192   tables in global memory
-  kNumClasses = 14
+  kClsC2 = 13,   // 8193..16384   thread-block cluster of 2 CTAs, table in distributed shared memory
+  kClsC4 = 14,   // 16385..32768  cluster of 4
+  kClsC8 = 15,   // 32769..65536  cluster of 8
+  kClsGiant = 16,  // > 65536     tables in global memory
+  kNumClasses = 17
 };
 
 __host__ __device__ inline int degree_class(int64_t deg) {
@@ -78,6 +81,9 @@ __host__ __device__ inline int degree_class(int64_t deg) {
   if (deg <= 2048) return kClsH4K;
   if (deg <= 4096) return kClsH8K;
   if (deg <= 8192) return kClsH16K;
+  if (deg <= 16384) return kClsC2;
+  if (deg <= 32768) return kClsC4;
+  if (deg <= 65536) return kClsC8;
   return kClsGiant;
 }
 

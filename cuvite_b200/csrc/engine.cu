@@ -124,11 +124,17 @@ struct cvb_engine {
   DevBuf<uint2> packed;                 // [nv_global] {label|singleton bit, community degree}
   DevBuf<int64_t> giant_layout;         // chunk_start[ng+1], table_start[ng+1]
   DevBuf<uint32_t> gmeta, gpiece_key;
-  DevBuf<uint4> gslots;
+  DevBuf<uint2> gslots;
   DevBuf<double> gpiece_gain, gchunk_gain;
   DevBuf<uint32_t> gchunk_key;
   DevBuf<int32_t> gchunk_owner;
+  // "big" = every vertex with deg > 8192 (cluster classes + giants): chunk layout of the first-sweep kernels
+  DevBuf<int64_t> big_layout;
+  DevBuf<int32_t> big_owner;
+  DevBuf<uint32_t> big_meta;
+  int64_t big_chunks = 0;
   int64_t giant_chunks = 0, giant_slots = 0;
+  bool use_cluster = false;    // CVB_CLUSTER=1: DSMEM cluster kernels for 8193..65536
   bool giant_direct = false;   // CVB_GIANT_DIRECT=1: giant entries go straight to the global tables
   bool use_first_sweep = true; // cvb env CVB_NO_FIRST_SWEEP=1 disables the singleton fast path
   bool rows_simple = false;    // every row holds each tail at most once (ascending)
@@ -221,9 +227,9 @@ int launch_sweep(cvb_engine *e) {
   if ((n = cnt2(kClsH512)) > 0) CVB_TRY((launch_warp<W, 1024>(e, p, lst(kClsH512), n)));
   if ((n = cnt2(kClsH2K)) > 0) CVB_TRY((launch_block<W, 4096, 256>(e, p, lst(kClsH2K), n)));
   if ((n = cnt2(kClsH8K)) > 0) CVB_TRY((launch_block<W, 16384, 1024>(e, p, lst(kClsH8K), n)));
-  if ((n = cnt(kClsGiant)) > 0) {
+  if ((n = e->class_start[kClsGiant + 1] - e->class_start[kClsC2]) > 0) {  // cluster classes + giants
     const int grid = static_cast<int>(n < e->giant_blocks ? n : e->giant_blocks);
-    k_sweep_block<W, 1024, 1024, true><<<grid, 1024, 0, e->stream>>>(p, lst(kClsGiant), (int)n, e->giant.p,
+    k_sweep_block<W, 1024, 1024, true><<<grid, 1024, 0, e->stream>>>(p, lst(kClsC2), (int)n, e->giant.p,
                                                                     e->giant_stride, e->giant_log2cap);
     e->launches++;
   }
@@ -250,6 +256,35 @@ int launch_hash(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const v
   return CVB_OK;
 }
 
+template <int CS>
+int launch_cluster(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const vid_t *list, int64_t n) {
+  const size_t smem = static_cast<size_t>(kClusterSlice) * 8 + 16;
+  static bool configured = false;
+  if (!configured) {
+    CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_cluster<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    configured = true;
+  }
+  int64_t nclusters = n;
+  const int64_t cap = e->num_sms / CS;
+  if (nclusters > cap) nclusters = cap;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(nclusters * CS));
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CVB_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_u32_cluster<CS>, p, list, static_cast<int>(n)));
+  e->launches++;
+  return CVB_OK;
+}
+
 // The CVB_WEIGHTS_U32 sweep: pack labels, then the degree-class kernels forked
 // over the auxiliary streams and joined back on the engine stream.
 int launch_sweep_u32(cvb_engine *e) {
@@ -262,6 +297,7 @@ int launch_sweep_u32(cvb_engine *e) {
   p.tails = e->tails.p;
   p.weights = reinterpret_cast<const uint32_t *>(e->weights.p);
   p.packed = e->packed.p;
+  p.cdeg = e->cdeg.p;
   p.vdeg = e->vdeg.p;
   p.constant = e->constant;
   p.base = static_cast<vid_t>(e->base);
@@ -291,19 +327,17 @@ int launch_sweep_u32(cvb_engine *e) {
     go(k_sweep_u32_first<32>, 32, kClsH256, kClsH1K, e->aux[2]);
     go(k_sweep_u32_first<8>, 8, kClsG16, kClsH128, e->aux[3]);
     go(k_sweep_u32_first<1>, 1, kClsG4, kClsG8, e->aux[3]);
-    if ((n = cnt(kClsGiant)) > 0) {
-      GiantTables gt;
-      gt.chunk_owner = e->gchunk_owner.p;
-      gt.chunk_start = e->giant_layout.p;
-      gt.table_start = e->giant_layout.p + (n + 1);
-      gt.slots = e->gslots.p; gt.gmeta = e->gmeta.p;
-      gt.piece_gain = e->gpiece_gain.p; gt.piece_key = e->gpiece_key.p;
-      int64_t g1 = e->giant_chunks < 8LL * e->num_sms ? e->giant_chunks : 8LL * e->num_sms;
-      k_sweep_u32_first_giant<<<static_cast<int>(g1), 512, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt,
-                                                                          e->giant_chunks, e->gchunk_gain.p,
-                                                                          e->gchunk_key.p);
+    if ((n = span(kClsC2, kClsGiant)) > 0) {  // every vertex above 8192 entries: chunked over the grid
+      GiantTables gt{};
+      gt.chunk_owner = e->big_owner.p;
+      gt.chunk_start = e->big_layout.p;
+      gt.table_start = e->big_layout.p + (n + 1);
+      gt.gmeta = e->big_meta.p;
+      int64_t g1 = e->big_chunks < 8LL * e->num_sms ? e->big_chunks : 8LL * e->num_sms;
+      k_sweep_u32_first_giant<<<static_cast<int>(g1), 512, 0, e->aux[1]>>>(p, lst(kClsC2), (int)n, gt, e->big_chunks,
+                                                                          e->gchunk_gain.p, e->gchunk_key.p);
       k_sweep_u32_first_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(
-          p, lst(kClsGiant), (int)n, gt, e->gchunk_gain.p, e->gchunk_key.p);
+          p, lst(kClsC2), (int)n, gt, e->gchunk_gain.p, e->gchunk_key.p);
       e->launches += 2;
     }
     for (int i = 0; i < cvb_engine::kAux; ++i) {
@@ -321,8 +355,17 @@ int launch_sweep_u32(cvb_engine *e) {
   if ((n = cnt(kClsH8K)) > 0) CVB_TRY((launch_hash<512, 4, 2, 2>(e, e->aux[0], p, lst(kClsH8K), n)));
   if ((n = cnt(kClsH4K)) > 0) CVB_TRY((launch_hash<256, 4, 2, 4>(e, e->aux[0], p, lst(kClsH4K), n)));
   if ((n = cnt(kClsH2K)) > 0) CVB_TRY((launch_hash<128, 4, 2, 8>(e, e->aux[0], p, lst(kClsH2K), n)));
-  // stream 1: giants
-  if ((n = cnt(kClsGiant)) > 0) {
+  // stream 1: vertices above 8192 entries.  Default: global (L2-resident) tables for all of
+  // them; CVB_CLUSTER=1 routes 8193..65536 to thread-block clusters with the table in
+  // distributed shared memory (correct, but DSMEM moves ~32 B per 4-byte atomic and
+  // measured slower on B200 — DESIGN.md section 5).
+  const int gcls = e->use_cluster ? kClsGiant : kClsC2;
+  if (e->use_cluster) {
+    if ((n = cnt(kClsC8)) > 0) CVB_TRY(launch_cluster<8>(e, e->aux[1], p, lst(kClsC8), n));
+    if ((n = cnt(kClsC4)) > 0) CVB_TRY(launch_cluster<4>(e, e->aux[1], p, lst(kClsC4), n));
+    if ((n = cnt(kClsC2)) > 0) CVB_TRY(launch_cluster<2>(e, e->aux[1], p, lst(kClsC2), n));
+  }
+  if ((n = e->class_start[kClsGiant + 1] - e->class_start[gcls]) > 0) {
     GiantTables gt;
     gt.chunk_owner = e->gchunk_owner.p;
     gt.chunk_start = e->giant_layout.p;
@@ -341,15 +384,15 @@ int launch_sweep_u32(cvb_engine *e) {
     }
     if (e->giant_direct) {
       int64_t g0 = e->giant_chunks < 4LL * e->num_sms ? e->giant_chunks : 4LL * e->num_sms;
-      k_sweep_u32_giant_insert_direct<<<static_cast<int>(g0), 512, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt,
+      k_sweep_u32_giant_insert_direct<<<static_cast<int>(g0), 512, 0, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
                                                                                   e->giant_chunks);
     } else {
-      k_sweep_u32_giant_insert<<<static_cast<int>(g1), 512, kGiantSmem, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt,
+      k_sweep_u32_giant_insert<<<static_cast<int>(g1), 512, kGiantSmem, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
                                                                                     e->giant_chunks);
     }
     int64_t g2 = pieces < 4LL * e->num_sms ? pieces : 4LL * e->num_sms;
-    k_sweep_u32_giant_eval<<<static_cast<int>(g2), 512, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n, gt, pieces);
-    k_sweep_u32_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(p, lst(kClsGiant), (int)n,
+    k_sweep_u32_giant_eval<<<static_cast<int>(g2), 512, 0, e->aux[1]>>>(p, lst(gcls), (int)n, gt, pieces);
+    k_sweep_u32_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(p, lst(gcls), (int)n,
                                                                                          gt);
     e->launches += 3;
   }
@@ -449,13 +492,13 @@ int post_graph(cvb_engine *e) {
   e->max_degree = static_cast<int64_t>(ent[kNumClasses]);
   e->local_weight = lw;
   // global-memory tables for the giant class
-  const int64_t ngiant = e->class_start[kClsGiant + 1] - e->class_start[kClsGiant];
-  if (ngiant > 0 && e->mode == CVB_WEIGHTS_F64) {
+  const int64_t nbig = e->class_start[kClsGiant + 1] - e->class_start[kClsC2];
+  if (nbig > 0 && e->mode == CVB_WEIGHTS_F64) {
     int lg = 14;
     while ((int64_t(1) << lg) < 2 * e->max_degree) ++lg;
     e->giant_log2cap = lg;
     e->giant_stride = ((sizeof(vid_t) + wbytes) << lg);
-    e->giant_blocks = static_cast<int>(ngiant < 2 * e->num_sms ? ngiant : 2 * e->num_sms);
+    e->giant_blocks = static_cast<int>(nbig < 2 * e->num_sms ? nbig : 2 * e->num_sms);
     CVB_TRY(e->giant.ensure(e->giant_stride * e->giant_blocks));
   }
   if (e->mode == CVB_WEIGHTS_U32) {
@@ -471,9 +514,29 @@ int post_graph(cvb_engine *e) {
     CVB_CUDA(cudaMemcpyAsync(&not_simple, e->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CVB_CUDA(cudaStreamSynchronize(st));
     e->rows_simple = not_simple == 0;
+    e->big_chunks = 0;
+    if (nbig > 0) {  // chunk layout over every vertex above 8192 entries (first-sweep kernels)
+      CVB_TRY(e->big_layout.ensure(2 * (nbig + 1)));
+      k_giant_layout<<<1, 32, 0, st>>>(e->offsets.p, e->list.p + e->class_start[kClsC2], (int)nbig, e->big_layout.p,
+                                       e->big_layout.p + (nbig + 1));
+      e->launches++;
+      int64_t totc = 0;
+      CVB_CUDA(cudaMemcpyAsync(&totc, e->big_layout.p + nbig, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      CVB_CUDA(cudaStreamSynchronize(st));
+      e->big_chunks = totc;
+      CVB_TRY(e->big_owner.ensure(totc + 1));
+      CVB_TRY(e->big_meta.ensure(3 * nbig + 4));
+      CVB_TRY(e->gchunk_gain.ensure(totc + 1));
+      CVB_TRY(e->gchunk_key.ensure(totc + 1));
+      CVB_CUDA(cudaMemsetAsync(e->big_meta.p, 0, (3 * nbig + 4) * sizeof(uint32_t), st));
+      k_giant_chunk_owner<<<static_cast<int>(nbig), 64, 0, st>>>(e->big_layout.p, (int)nbig, e->big_owner.p);
+      e->launches++;
+    }
+    const int gcls = e->use_cluster ? kClsGiant : kClsC2;
+    const int64_t ngiant = e->class_start[kClsGiant + 1] - e->class_start[gcls];  // global-table vertices
     if (ngiant > 0) {
       CVB_TRY(e->giant_layout.ensure(2 * (ngiant + 1)));
-      k_giant_layout<<<1, 32, 0, st>>>(e->offsets.p, e->list.p + e->class_start[kClsGiant], (int)ngiant,
+      k_giant_layout<<<1, 32, 0, st>>>(e->offsets.p, e->list.p + e->class_start[gcls], (int)ngiant,
                                        e->giant_layout.p, e->giant_layout.p + (ngiant + 1));
       e->launches++;
       int64_t tot[2];
@@ -487,8 +550,6 @@ int post_graph(cvb_engine *e) {
       CVB_TRY(e->gmeta.ensure(3 * ngiant + 4));
       CVB_TRY(e->gpiece_gain.ensure(e->giant_slots / kGiantPiece + 1));
       CVB_TRY(e->gpiece_key.ensure(e->giant_slots / kGiantPiece + 1));
-      CVB_TRY(e->gchunk_gain.ensure(e->giant_chunks + 1));
-      CVB_TRY(e->gchunk_key.ensure(e->giant_chunks + 1));
       CVB_TRY(e->gchunk_owner.ensure(e->giant_chunks + 1));
       k_giant_chunk_owner<<<static_cast<int>(ngiant), 64, 0, st>>>(e->giant_layout.p, (int)ngiant, e->gchunk_owner.p);
       e->launches++;
@@ -596,6 +657,7 @@ cvb_engine *cvb_create(void *stream) {
   e->device = dev;
   if (const char *s = getenv("CVB_NO_FIRST_SWEEP")) e->use_first_sweep = !(s[0] == '1');
   if (const char *s = getenv("CVB_GIANT_DIRECT")) e->giant_direct = (s[0] == '1');
+  if (const char *s = getenv("CVB_CLUSTER")) e->use_cluster = (s[0] == '1');
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) e->num_sms = sms;
   if (stream) {
@@ -638,7 +700,8 @@ void cvb_destroy(cvb_engine *e) {
   e->h_sums.release(); e->staging.release(); e->staging2.release(); e->giant.release(); e->h_stage.release();
   e->packed.release(); e->giant_layout.release(); e->gslots.release();
   e->gmeta.release(); e->gpiece_key.release(); e->gpiece_gain.release(); e->gchunk_gain.release();
-  e->gchunk_key.release(); e->gchunk_owner.release();
+  e->gchunk_key.release(); e->gchunk_owner.release(); e->big_layout.release(); e->big_owner.release();
+  e->big_meta.release();
   for (int i = 0; i < cvb_engine::kAux; ++i) {
     if (e->aux[i]) cudaStreamDestroy(e->aux[i]);
     if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
@@ -795,6 +858,16 @@ double cvb_modularity_from_sums(const cvb_engine *e, const double sums[2]) {
   return (sums[0] * c) - (sums[1] * c * c);  // louvain.cpp:2472-2473
 }
 
+int cvb_rebuild_and_reduce_async(cvb_engine *e) {
+  CVB_CHECK(e && e->phase_ready, CVB_ERR_STATE, "cvb_rebuild_and_reduce: no phase");
+  CVB_CHECK(e->nvl != e->nvg, CVB_ERR_STATE, "cvb_rebuild_and_reduce is the N > 1 path");
+  cudaStream_t st = e->stream;
+  k_apply_label_diff<<<grid_for(e->nvg, 256), 256, 0, st>>>(e->nvg, e->glabels_curr(), e->glabels_next(),
+                                                            e->vdeg_global.p, e->cdeg.p, e->csize.p);
+  e->launches++;
+  return apply_reduce_zero_deltas(e);
+}
+
 int cvb_rebuild_and_reduce(cvb_engine *e, double sums[2]) {
   CVB_CHECK(e && e->phase_ready && sums, CVB_ERR_STATE, "cvb_rebuild_and_reduce: no phase");
   CVB_CHECK(e->nvl != e->nvg, CVB_ERR_STATE, "cvb_rebuild_and_reduce is the N > 1 path");
@@ -886,6 +959,7 @@ void *cvb_buffer(cvb_engine *e, int which) {
     case CVB_BUF_LABELS_GLOBAL: return const_cast<vid_t *>(e->sweep_labels());
     case CVB_BUF_LABELS_GLOBAL_NEXT: return e->nvl == e->nvg ? e->lab[e->targ].p : e->glabels_next();
     case CVB_BUF_VDEG_GLOBAL: return e->nvl == e->nvg ? e->vdeg.p : e->vdeg_global.p;
+    case CVB_BUF_SUMS: return e->d_sums.p;
     case CVB_BUF_LABELS_CURR: return e->lab[e->curr].p;
     case CVB_BUF_LABELS_TARGET: return e->lab[e->targ].p;
     case CVB_BUF_LABELS_PAST: return e->lab[e->past].p;

@@ -34,6 +34,7 @@ struct SweepU32Params {
   const vid_t *__restrict__ tails;      // [ne]
   const uint32_t *__restrict__ weights; // [ne]
   const uint2 *__restrict__ packed;     // [nv_global] {label | singleton<<31, degree of that community}
+  const double *__restrict__ cdeg;      // [nv_global] community degrees (giant-table evaluation only)
   const double *__restrict__ vdeg;      // [nv_local]
   double constant;
   vid_t base;
@@ -540,6 +541,233 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
 }
 
 // ---------------------------------------------------------------------------
+// deg 8193..65536: one THREAD-BLOCK CLUSTER per vertex (2, 4 or 8 CTAs on as many
+// SMs), the hash table distributed over the cluster's shared memories (DSMEM).
+// CTA r streams entries [r*8192, (r+1)*8192) of the adjacency; a key's slot
+// lives in the CTA named by the top bits of its hash and is claimed / added to
+// with shared::cluster atomics, so the whole accumulation stays on chip and no
+// global table, no L2 atomic and no second pass over memory is needed.
+// Per CTA: keys[16384] wts[16384] (128 KB), meta[4]; rank 0 also gathers the
+// per-CTA candidates.
+// ---------------------------------------------------------------------------
+constexpr int kClusterSliceLog2 = 14;  // 16384 slots per CTA
+constexpr int kClusterSlice = 1 << kClusterSliceLog2;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nclusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t d;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(addr), "r"(rank));
+  return d;
+}
+__device__ __forceinline__ uint32_t atomc_cas(uint32_t addr, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared::cluster.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ void redc_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared::cluster.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ldc_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stc_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stc_f64(uint32_t addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int CS>
+__global__ void __launch_bounds__(1024, 1) k_sweep_u32_cluster(SweepU32Params p, const vid_t *__restrict__ list, int n) {
+  constexpr int TPB = 1024, KC = 4, NCH = 2, K = KC * NCH;
+  constexpr int kLog2Cap = kClusterSliceLog2 + (CS == 2 ? 1 : CS == 4 ? 2 : 3);
+  constexpr uint32_t capb = kClusterSlice * 4u;          // bytes of one keys[] slice
+  constexpr uint32_t maskw = (1u << kLog2Cap) - 1u;      // slot mask over the whole cluster
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  __shared__ double red_g[32];
+  __shared__ uint32_t red_id[32];
+  __shared__ double cl_g[8];     // rank 0: one candidate per CTA
+  __shared__ uint32_t cl_id[8];
+  uint32_t *keys = smem_u32, *wts = smem_u32 + kClusterSlice, *meta = smem_u32 + 2 * kClusterSlice;
+  const uint32_t kaddr = smem_addr(keys);
+  const uint32_t maddr = smem_addr(meta);
+  const uint32_t rank = cluster_ctarank();
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = threadIdx.x >> 5;
+  const int tid = threadIdx.x;
+  for (int s = tid; s < kClusterSlice; s += TPB) {
+    keys[s] = kEmptyKeyU;
+    wts[s] = 0u;
+  }
+  if (tid < 4) meta[tid] = 0u;
+  cluster_sync_all();
+  const uint32_t maddr0 = mapa_u32(maddr, 0);  // rank 0's meta: {-, selfloop, counter0, -}
+
+  for (int64_t item = cluster_id_x(); item < n; item += cluster_nclusters_x()) {
+    const vid_t v = list[item];
+    const eid_t e0 = p.offsets[v], e1 = p.offsets[v + 1];
+    const int deg = static_cast<int>(e1 - e0);
+    const vid_t self = v + p.base;
+    const uint2 me = p.packed[self];
+    const uint32_t cc = me.x & kLabelMask;
+    const double vd = p.vdeg[v];
+    const vid_t *__restrict__ row_tails = p.tails + e0;
+    const uint32_t *__restrict__ row_weights = p.weights + e0;
+    const int i0 = static_cast<int>(rank) * (TPB * K);  // this CTA's window of the row
+
+    uint32_t ckey[K], cay[K], caddr[K];
+    uint32_t freshmask = 0u, ownsum = 0u, selfsum = 0u;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t key[KC], w[KC];
+      vid_t tail[KC];
+      uint32_t validm = 0u;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int i = i0 + tid + (c * KC + k) * TPB;
+        tail[k] = self;
+        w[k] = 0u;
+        if (i < deg) {
+          tail[k] = __ldcs(&row_tails[i]);
+          w[k] = __ldcs(&row_weights[i]);
+          validm |= 1u << k;
+        }
+      }
+      uint32_t active = 0u;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const uint2 pk = p.packed[tail[k]];
+        const bool valid = (validm >> k) & 1u;
+        key[k] = valid ? pk.x : kEmptyKeyU;
+        cay[c * KC + k] = pk.y;
+        const bool own = (key[k] & kLabelMask) == cc;
+        ownsum += own ? w[k] : 0u;
+        selfsum += (valid && tail[k] == self) ? w[k] : 0u;
+        active |= (valid && !own) ? (1u << k) : 0u;
+      }
+      // claim: all first probes in flight, then round-outer retries (one DSMEM round trip per round)
+      uint32_t sl[KC], old[KC], addr[KC];
+      uint32_t pend = 0u, fresh = 0u;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        sl[k] = hash_key(key[k], kLog2Cap);
+        addr[k] = mapa_u32(kaddr, sl[k] >> kClusterSliceLog2) + ((sl[k] & (kClusterSlice - 1)) << 2);
+        old[k] = key[k];
+        if (active & (1u << k)) old[k] = atomc_cas(addr[k], kEmptyKeyU, key[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const bool act = (active >> k) & 1u;
+        fresh |= (act && old[k] == kEmptyKeyU) ? (1u << k) : 0u;
+        pend |= (act && old[k] != kEmptyKeyU && old[k] != key[k]) ? (1u << k) : 0u;
+      }
+      while (pend) {
+#pragma unroll
+        for (int k = 0; k < KC; ++k)
+          if (pend & (1u << k)) {
+            sl[k] = (sl[k] + hash_step(key[k], kLog2Cap)) & maskw;
+            addr[k] = mapa_u32(kaddr, sl[k] >> kClusterSliceLog2) + ((sl[k] & (kClusterSlice - 1)) << 2);
+            old[k] = atomc_cas(addr[k], kEmptyKeyU, key[k]);
+          }
+#pragma unroll
+        for (int k = 0; k < KC; ++k)
+          if (pend & (1u << k)) {
+            if (old[k] == kEmptyKeyU) {
+              fresh |= 1u << k;
+              pend &= ~(1u << k);
+            } else if (old[k] == key[k]) {
+              pend &= ~(1u << k);
+            }
+          }
+      }
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        if (active & (1u << k)) redc_add(addr[k] + capb, w[k]);
+        ckey[c * KC + k] = key[k];
+        caddr[c * KC + k] = addr[k];
+      }
+      freshmask |= fresh << (c * KC);
+    }
+    {
+      const uint32_t c0u = __reduce_add_sync(0xffffffffu, ownsum);
+      const uint32_t slu = __reduce_add_sync(0xffffffffu, selfsum);
+      if (lane == 0) {
+        if (c0u) redc_add(maddr0 + 8, c0u);
+        if (slu) redc_add(maddr0 + 4, slu);
+      }
+    }
+    cluster_sync_all();  // every insert of every CTA has landed
+
+    const double counter0 = static_cast<double>(ldc_u32(maddr0 + 8));
+    const double eix = counter0 - static_cast<double>(ldc_u32(maddr0 + 4));
+    const double ax = static_cast<double>(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+#pragma unroll
+    for (int q = 0; q < K; ++q)
+      if (freshmask & (1u << q)) {
+        const uint32_t tot = ldc_u32(caddr[q] + capb);
+        stc_u32(caddr[q], kEmptyKeyU);
+        stc_u32(caddr[q] + capb, 0u);
+        const double g2 = modularity_gain(static_cast<double>(tot), eix, vd, static_cast<double>(cay[q]), ax, p.constant);
+        if (better_u(g2, ckey[q], g, id)) {
+          g = g2;
+          id = ckey[q];
+        }
+      }
+    double wg;
+    uint32_t wid = warp_argmax(g, id, &wg);
+    if (lane == 0) {
+      red_g[wib] = wg;
+      red_id[wib] = wid;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < TPB / 32; ++i)
+        if (better_u(red_g[i], red_id[i], wg, wid)) {
+          wg = red_g[i];
+          wid = red_id[i];
+        }
+      stc_f64(mapa_u32(smem_addr(&cl_g[rank]), 0), wg);
+      stc_u32(mapa_u32(smem_addr(&cl_id[rank]), 0), wid);
+    }
+    cluster_sync_all();  // candidates and slot clears visible cluster-wide
+    if (rank == 0 && tid == 0) {
+      wg = cl_g[0];
+      wid = cl_id[0];
+      for (int r = 1; r < CS; ++r)
+        if (better_u(cl_g[r], cl_id[r], wg, wid)) {
+          wg = cl_g[r];
+          wid = cl_id[r];
+        }
+      commit_vertex_u32(p, v, me.x, wg, wid, vd, counter0);
+      meta[1] = 0u;
+      meta[2] = 0u;
+    }
+    cluster_sync_all();  // meta reset before the next vertex's sums arrive
+  }
+}
+
+// ---------------------------------------------------------------------------
 // deg > 8192: tables in global memory, three kernels.
 //   k_sweep_u32_giant_insert : blocks take 4096-entry chunks of giant
 //       adjacencies (chunk -> vertex by binary search in chunk_start) and
@@ -558,7 +786,7 @@ struct GiantTables {
   const int32_t *__restrict__ chunk_owner;  // [total_chunks] giant index of every chunk
   const int64_t *__restrict__ chunk_start;  // [ngiant+1] prefix of chunks per vertex
   const int64_t *__restrict__ table_start;  // [ngiant+1] prefix of table slots per vertex
-  uint4 *__restrict__ slots;  // {key, weight, community degree, -}: one 16-byte sector-friendly record
+  uint2 *__restrict__ slots;  // {key, weight}: 8-byte records keep the tables of all big vertices L2-resident
   uint32_t *__restrict__ gmeta;
   double *__restrict__ piece_gain;   // [total_slots / kGiantPiece]
   uint32_t *__restrict__ piece_key;  // [total_slots / kGiantPiece]
@@ -581,10 +809,10 @@ __global__ void k_giant_layout(const eid_t *__restrict__ offsets, const vid_t *_
   table_start[n] = s;
 }
 
-__global__ void k_giant_init_slots(uint4 *__restrict__ slots, int64_t n) {
+__global__ void k_giant_init_slots(uint2 *__restrict__ slots, int64_t n) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    slots[i] = make_uint4(kEmptyKeyU, 0u, 0u, 0u);
+    slots[i] = make_uint2(kEmptyKeyU, 0u);
 }
 
 __global__ void k_giant_chunk_owner(const int64_t *__restrict__ chunk_start, int n, int32_t *__restrict__ owner) {
@@ -605,9 +833,9 @@ __device__ __forceinline__ int giant_owner(const int64_t *__restrict__ start, in
 // Global-table twin of table_insert_chunk: K independent L2 atomics in flight,
 // collided entries retry in their own short loops.
 template <int K>
-__device__ __forceinline__ void gtable_insert_chunk(uint4 *__restrict__ slots, const uint32_t (&key)[K],
-                                                    const uint32_t (&ay)[K], const uint32_t (&w)[K], uint32_t active,
-                                                    int log2cap, uint32_t mask) {
+__device__ __forceinline__ void gtable_insert_chunk(uint2 *__restrict__ slots, const uint32_t (&key)[K],
+                                                    const uint32_t (&w)[K], uint32_t active, int log2cap,
+                                                    uint32_t mask) {
   uint32_t old[K], sl[K];
   uint32_t fresh = 0u, pend = 0u;
 #pragma unroll
@@ -644,10 +872,8 @@ __device__ __forceinline__ void gtable_insert_chunk(uint4 *__restrict__ slots, c
   }
 #pragma unroll
   for (int k = 0; k < K; ++k)
-    if (active & (1u << k)) {
-      atomicAdd(&slots[sl[k]].y, w[k]);
-      if (fresh & (1u << k)) slots[sl[k]].z = ay[k];
-    }
+    if (active & (1u << k)) atomicAdd(&slots[sl[k]].y, w[k]);
+  (void)fresh;
 }
 
 // One 4096-entry chunk per block iteration: the chunk is first merged in a
@@ -744,7 +970,7 @@ __global__ void __launch_bounds__(512, 2) k_sweep_u32_giant_insert(SweepU32Param
         sts_u32(a + capb, 0u);
       }
     }
-    gtable_insert_chunk<K>(gt.slots + tbase, ckey, cay, tot, freshmask, glog2, gmask);
+    gtable_insert_chunk<K>(gt.slots + tbase, ckey, tot, freshmask, glog2, gmask);
     __syncthreads();
   }
 }
@@ -797,7 +1023,7 @@ __global__ void __launch_bounds__(512, 4) k_sweep_u32_giant_insert_direct(SweepU
       selfsum += (valid && tail[k] == self) ? w[k] : 0u;
       active |= (valid && !own) ? (1u << k) : 0u;
     }
-    gtable_insert_chunk<K>(gt.slots + tbase, key, ay, w, active, glog2, gmask);
+    gtable_insert_chunk<K>(gt.slots + tbase, key, w, active, glog2, gmask);
     const uint32_t c0u = __reduce_add_sync(0xffffffffu, ownsum);
     const uint32_t slu = __reduce_add_sync(0xffffffffu, selfsum);
     if (lane == 0) {
@@ -826,15 +1052,23 @@ __global__ void __launch_bounds__(512) k_sweep_u32_giant_eval(SweepU32Params p, 
     double g = -1.0;
     uint32_t id = kLabelMask;
 #pragma unroll
-    for (int j0 = 0; j0 < kGiantPiece / 512; j0 += 4) {  // four 16-byte records in flight per thread
-      uint4 r[4];
+    for (int j0 = 0; j0 < kGiantPiece / 512; j0 += 4) {  // four records (and their degree gathers) in flight
+      uint2 r[4];
+      double ayv[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) r[j] = __ldcg(&gt.slots[s0 + threadIdx.x + (j0 + j) * 512]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        ayv[j] = 0.0;
         if (r[j].x != kEmptyKeyU) {
-          gt.slots[s0 + threadIdx.x + (j0 + j) * 512] = make_uint4(kEmptyKeyU, 0u, 0u, 0u);
-          const double g2 = modularity_gain(static_cast<double>(r[j].y), eix, vd, static_cast<double>(r[j].z), ax, p.constant);
+          ayv[j] = p.cdeg[r[j].x & kLabelMask];
+          gt.slots[s0 + threadIdx.x + (j0 + j) * 512] = make_uint2(kEmptyKeyU, 0u);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (r[j].x != kEmptyKeyU) {
+          const double g2 = modularity_gain(static_cast<double>(r[j].y), eix, vd, ayv[j], ax, p.constant);
           if (better_u(g2, r[j].x, g, id)) {
             g = g2;
             id = r[j].x;

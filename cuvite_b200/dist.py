@@ -99,6 +99,13 @@ class DistLouvain:
         e.sweep()
         if self.world > 1 and self.labels_only:
             self._all_gather_rows(tensor_of(e, "labels_global_next"), tensor_of(e, "labels_target"))
+            if hasattr(e, "rebuild_and_reduce_async"):  # sums stay on the device: one read-back per sweep
+                e.rebuild_and_reduce_async()
+                s = tensor_of(e, "sums")
+                self._all_reduce(s)
+                sums = s.cpu().numpy()
+                c = self.constant
+                return (sums[0] * c) - (sums[1] * c * c)
             sums = e.rebuild_and_reduce()
         else:
             if self.world > 1:

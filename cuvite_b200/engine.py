@@ -26,8 +26,8 @@ from ._lib import GraphInfo, check
 WEIGHTS_U32, WEIGHTS_F64 = 1, 2
 LABELS_PAST, LABELS_CURR, LABELS_TARGET = 0, 1, 2
 BUF = dict(labels_global=0, labels_curr=1, labels_target=2, labels_past=3, cdeg=4, csize=5, ddeg=6, dsize=7,
-           vdeg=8, cw=9, offsets=10, tails=11, weights=12, labels_global_next=13, vdeg_global=14)
-CLASS_NAMES = ["deg0", "d4", "d8", "d16", "d32", "d64", "d128", "d256", "d512", "d1k", "d2k", "d4k", "d8k", "giant"]
+           vdeg=8, cw=9, offsets=10, tails=11, weights=12, labels_global_next=13, vdeg_global=14, sums=15)
+CLASS_NAMES = ["deg0", "d4", "d8", "d16", "d32", "d64", "d128", "d256", "d512", "d1k", "d2k", "d4k", "d8k", "c16k", "c32k", "c64k", "giant"]
 
 
 def _ptr(a):
@@ -132,6 +132,9 @@ class GpuGraph:
         check(self._L.cvb_rebuild_and_reduce(self._h, sums), "rebuild_and_reduce")
         return np.array([sums[0], sums[1]])
 
+    def rebuild_and_reduce_async(self):
+        check(self._L.cvb_rebuild_and_reduce_async(self._h), "rebuild_and_reduce_async")
+
     def modularity_from_sums(self, sums) -> float:
         s = (C.c_double * 2)(float(sums[0]), float(sums[1]))
         return self._L.cvb_modularity_from_sums(self._h, s)
@@ -196,7 +199,7 @@ class GpuGraph:
                       labels_target=(gi.nv_local, "<i4"), labels_past=(gi.nv_local, "<i4"),
                       cdeg=(gi.nv_global, "<f8"), csize=(gi.nv_global, "<i4"), ddeg=(gi.nv_global, "<f8"),
                       dsize=(gi.nv_global, "<i4"), vdeg=(gi.nv_local, "<f8"), cw=(gi.nv_local, "<f8"),
-                      labels_global_next=(gi.nv_global, "<i4"), vdeg_global=(gi.nv_global, "<f8"),
+                      labels_global_next=(gi.nv_global, "<i4"), vdeg_global=(gi.nv_global, "<f8"), sums=(2, "<f8"),
                       offsets=(gi.nv_local + 1, "<i8"), tails=(gi.ne_local, "<i4"),
                       weights=(gi.ne_local, "<u4" if gi.weight_mode == WEIGHTS_U32 else "<f8"))
         n, ts = shapes[name]

@@ -87,8 +87,8 @@ typedef struct {
   int64_t nv_local, base, nv_global, ne_local;
   int32_t weight_mode;        /* CVB_WEIGHTS_* */
   int32_t num_classes;        /* degree classes in use */
-  int64_t class_count[16];    /* vertices per degree class */
-  int64_t class_entries[16];  /* CSR entries per degree class */
+  int64_t class_count[24];    /* vertices per degree class */
+  int64_t class_entries[24];  /* CSR entries per degree class */
   int64_t max_degree;
   double local_weight;        /* sum of local vertex degrees (the 2m share) */
 } cvb_graph_info;
@@ -128,6 +128,9 @@ int cvb_apply_and_reduce(cvb_engine *e, double sums[2]);
  * and returns the same two sums as cvb_apply_and_reduce.  cvb_rotate_labels
  * then also swaps the two global label arrays. */
 int cvb_rebuild_and_reduce(cvb_engine *e, double sums[2]);
+/* Same, asynchronous: the sums stay in CVB_BUF_SUMS on the device (so that the
+ * host side can all-reduce them with NCCL and read back once). */
+int cvb_rebuild_and_reduce_async(cvb_engine *e);
 
 /* Q = e*c - a2*c*c (louvain.cpp:2472-2473) from globally reduced sums. */
 double cvb_modularity_from_sums(const cvb_engine *e, const double sums[2]);
@@ -169,7 +172,8 @@ enum {
   CVB_BUF_TAILS = 11,        /* int32[ne_local]                                     */
   CVB_BUF_WEIGHTS = 12,      /* uint32 or double [ne_local], see weight_mode        */
   CVB_BUF_LABELS_GLOBAL_NEXT = 13, /* int32[nv_global] gather target for the NEXT labels (N>1) */
-  CVB_BUF_VDEG_GLOBAL = 14   /* double[nv_global] every vertex's degree (N>1, replicated)   */
+  CVB_BUF_VDEG_GLOBAL = 14,  /* double[nv_global] every vertex's degree (N>1, replicated)   */
+  CVB_BUF_SUMS = 15          /* double[2] device copy of the last {sum clusterWeight, sum degree^2} */
 };
 void *cvb_buffer(cvb_engine *e, int which);
 void *cvb_stream(cvb_engine *e);

@@ -278,3 +278,40 @@ def test_reference_main_runs_on_our_plugin(tmp_path):
         outs[tag] = (levels, open(f + ".communities").read())
     assert outs["cpu"][0] == outs["gpu"][0]
     assert outs["cpu"][1] == outs["gpu"][1]
+
+
+@pytest.mark.parametrize("cluster", [False, True])
+def test_true_giant_hub_matches_oracle(oracle, cluster, monkeypatch):
+    """Vertices above 8192 entries: global-table path (default) and the thread-block-cluster /
+    distributed-shared-memory path (CVB_CLUSTER=1), incl. one vertex above 65536 entries."""
+    import torch
+    from cuvite_b200 import graphgen as gg
+    from cuvite_b200.engine import GpuGraph
+    monkeypatch.setenv("CVB_CLUSTER", "1" if cluster else "0")
+    gpu = GpuGraph()
+    nv = 90000
+    bg = gg.erdos_renyi(nv, 6.0, seed=11)
+    src = np.repeat(np.arange(nv, dtype=np.int64), np.diff(bg.offsets.numpy()))
+    dst = bg.tails.numpy()
+    es, ed = [src], [dst]
+    for hub, deg in ((0, nv - 1), (1, 40000), (2, 20000), (3, 10000)):
+        es.append(np.full(deg, hub, np.int64))
+        ed.append((np.arange(deg, dtype=np.int64) * 7919 + 11 * hub + 13) % nv)
+    g = gg.csr_from_pairs(nv, torch.from_numpy(np.concatenate(es)), torch.from_numpy(np.concatenate(ed)))
+    o, t, w = g.offsets.numpy(), g.tails.numpy(), g.weights.numpy()
+    want = oracle.phase(o, t, w, trace=8)
+    gpu.upload(o, t, w)
+    info = gpu.info()
+    from cuvite_b200.engine import CLASS_NAMES
+    counts = dict(zip(CLASS_NAMES, list(info.class_count)[:info.num_classes]))
+    assert counts["giant"] >= 1 and counts["c64k"] >= 1 and counts["c32k"] >= 1 and counts["c16k"] >= 1, counts
+    gpu.phase_begin()
+    for k in range(want.iters):
+        gpu.sweep()
+        assert np.array_equal(gpu.labels(2), want.targets[k]), f"iteration {k + 1}"
+        sums = gpu.apply_and_reduce()
+        assert gpu.modularity_from_sums(sums) == want.qs[k]
+        gpu.rotate_labels()
+    q, iters = gpu.phase_run()
+    assert (q, iters) == (want.q, want.iters) and np.array_equal(gpu.labels(0), want.cvect)
+    gpu.close()
