@@ -158,20 +158,26 @@ def bench_single(args):
         sums = gpu.apply_and_reduce()
         q = gpu.modularity_from_sums(sums)
         state["sweep_ms"].append(gpu.last_sweep_ms())
+        state["it"] += 1
+        state["iter_in_phase"].append(state["it"])
         if q - state["prev"] < 1e-6:  # phase converged: restart from singletons (inside the timed region)
             gpu.phase_reset()
             state["prev"] = -1.0
             state["phases"] += 1
+            state["it"] = 0
         else:
             state["prev"] = q
             gpu.rotate_labels()
 
+    def fresh_state():
+        return {"prev": -1.0, "sweep_ms": [], "phases": 0, "it": 0, "iter_in_phase": []}
+
     gpu.phase_begin()
-    st = {"prev": -1.0, "sweep_ms": [], "phases": 0}
+    st = fresh_state()
     for _ in range(max(args.warmup, 3)):
         step(st)
     gpu.phase_reset()
-    st = {"prev": -1.0, "sweep_ms": [], "phases": 0}
+    st = fresh_state()
     launches0 = gpu.launch_count
     sampler = ClockSampler(0)
     sampler.start()
@@ -189,6 +195,13 @@ def bench_single(args):
     bytes_sweep = 12 * ne + 40 * nv
     peak, peak_src = measured_peak_gbs()
     achieved = bytes_sweep / (sweep_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if scale == BASE_SCALE and os.path.exists(tpath):  # ncu dram__bytes of the same command, committed
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["mean_sweep_dram_bytes"], "profiles/r01_traffic.json (1 table-free + 3 hash sweeps)"
+    first_ms = [m for i, m in enumerate(st["sweep_ms"]) if st["iter_in_phase"][i] == 1]
+    later_ms = [m for i, m in enumerate(st["sweep_ms"]) if st["iter_in_phase"][i] > 1]
 
     # ---- end to end through the plugin call with pinned host buffers -----------
     o_h = g.offsets.cpu().numpy()
@@ -208,11 +221,14 @@ def bench_single(args):
                                                        ("udg", np.float64), ("cw", np.float64))}
     o_pin = pinned(o_h)
 
+    tb = {k: torch.from_numpy(v) for k, v in bufs.items()}  # same memory; torch's host ops are threaded
+    t_vdeg, t_iota = torch.from_numpy(vdeg), torch.arange(nv, dtype=torch.int64)
+
     def e2e_reset():
-        bufs["past"][:] = np.arange(nv)
-        bufs["curr"][:] = bufs["past"]
-        bufs["csize"][:] = 1
-        bufs["cdeg"][:] = vdeg
+        tb["past"].copy_(t_iota)
+        tb["curr"].copy_(t_iota)
+        tb["csize"].fill_(1)
+        tb["cdeg"].copy_(t_vdeg)
 
     def e2e_steps(k):
         prev, it, uploads = -1.0, 0, 0
@@ -220,14 +236,14 @@ def bench_single(args):
         for _ in range(k):
             it += 1
             uploads += it == 1
-            bufs["cw"][:] = 0  # distCleanCWandCU, louvain.cpp:664
-            bufs["usz"][:] = 0
-            bufs["udg"][:] = 0
+            tb["cw"].zero_()  # distCleanCWandCU, louvain.cpp:664
+            tb["usz"].zero_()
+            tb["udg"].zero_()
             gpu_for_louvain_iteration(nv, o_pin, edges_p, bufs["curr"], bufs["target"], vdeg, bufs["csize"],
                                       bufs["cdeg"], bufs["usz"], bufs["udg"], {}, {}, {}, const, bufs["cw"], 0,
                                       it, gpu)
-            np.add(bufs["csize"], bufs["usz"], out=bufs["csize"])  # distUpdateLocalCinfo
-            np.add(bufs["cdeg"], bufs["udg"], out=bufs["cdeg"])
+            tb["csize"].add_(tb["usz"])  # distUpdateLocalCinfo, louvain.cpp:679
+            tb["cdeg"].add_(tb["udg"])
             le = gpu_reduce_mod(bufs["cdeg"], bufs["cw"], gpu, nv)
             q = le[0] * const - le[1] * const * const
             if q - prev < 1e-6:
@@ -236,6 +252,7 @@ def bench_single(args):
             else:
                 prev = q
                 bufs["past"], bufs["curr"], bufs["target"] = bufs["curr"], bufs["target"], bufs["past"]
+                tb["past"], tb["curr"], tb["target"] = tb["curr"], tb["target"], tb["past"]
         return uploads
 
     e2e_steps(2)
@@ -281,12 +298,15 @@ def bench_single(args):
                        "undirected_edges": ne // 2, "parallelism": "1 GPU",
                        "l2": "inputs (8 B x entries = %d MB) larger than the 126 MB L2; no flush" % (8 * ne >> 20),
                        "sweep_kernels_ms": sweep_ms, "first_sweep_ms": st["sweep_ms"][0],
+                       "first_iteration_sweeps_ms": statistics.mean(first_ms) if first_ms else None,
+                       "later_iteration_sweeps_ms": statistics.mean(later_ms) if later_ms else None,
                        "phase_restarts_in_timed_region": st["phases"],
                        "classes": {n: int(info.class_count[i]) for i, n in
                                    enumerate(CLASS_NAMES[:info.num_classes])}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "kernel": "sweep kernel group (all degree-class kernels of one sweep), 12E+40V bytes"},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "sweep kernel group (label pack + all degree-class kernels of one sweep), "
+                                   "12E+40V algorithmic bytes, CUDA events on the engine stream"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
                     "d2h_bytes_per_step": int(d2h),

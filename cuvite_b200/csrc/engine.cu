@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -63,6 +64,26 @@ struct HostBuf {  // pinned staging
     cap = 0;
   }
 };
+
+// Small host-side parallel loop for the "+=" contract of the plugin call
+// (localCupdate / remoteCupdate are ADDED to, louvain.cpp:2307-2376).
+template <typename F>
+static void host_parallel_for(int64_t n, F body) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = static_cast<int>(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+  if (n < (1 << 16) || nt <= 1) {
+    body(0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  const int64_t chunk = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    const int64_t lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    if (lo >= hi) break;
+    th.emplace_back([=]() { body(lo, hi); });
+  }
+  for (auto &x : th) x.join();
+}
 
 static inline int grid_for(int64_t n, int block, int max_blocks = 148 * 16) {
   int64_t g = (n + block - 1) / block;
@@ -1079,10 +1100,12 @@ int cvb_louvain_iteration(cvb_engine *e, int64_t nv, int64_t base, int64_t nv_gl
   CVB_CUDA(cudaStreamSynchronize(st));
   const int64_t *h_dsz = reinterpret_cast<const int64_t *>(hp);
   const double *h_ddg = reinterpret_cast<const double *>(hp + nv * 8);
-  for (int64_t i = 0; i < nv; ++i) {
-    local_cupd_size[i] += h_dsz[i];
-    local_cupd_deg[i] += h_ddg[i];
-  }
+  host_parallel_for(nv, [=](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
+      local_cupd_size[i] += h_dsz[i];
+      local_cupd_deg[i] += h_ddg[i];
+    }
+  });
   if (n_rcomm > 0 && e->nvl != e->nvg) {
     const int64_t *h_rsz = reinterpret_cast<const int64_t *>(hp + nv * 16);
     const double *h_rdg = reinterpret_cast<const double *>(hp + nv * 16 + n_rcomm * 8);

@@ -259,6 +259,21 @@ __device__ __forceinline__ uint32_t atoms_cas(uint32_t addr, uint32_t cmp, uint3
   asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(cmp), "r"(val) : "memory");
   return old;
 }
+// Predicated forms (@p atom / @p red): no branch, no BSSY/BSYNC around a single memory op.
+__device__ __forceinline__ uint32_t atoms_cas_if(bool pred, uint32_t addr, uint32_t cmp, uint32_t val, uint32_t dflt) {
+  uint32_t old;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\tmov.u32 %0, %5;\n\t@p atom.shared.cas.b32 %0, [%1], %2, %3;\n\t}"
+      : "=r"(old)
+      : "r"(addr), "r"(cmp), "r"(val), "r"(static_cast<uint32_t>(pred)), "r"(dflt)
+      : "memory");
+  return old;
+}
+__device__ __forceinline__ void reds_add_if(bool pred, uint32_t addr, uint32_t v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v),
+               "r"(static_cast<uint32_t>(pred))
+               : "memory");
+}
 __device__ __forceinline__ void reds_add(uint32_t addr, uint32_t v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -319,8 +334,7 @@ __device__ __forceinline__ uint32_t table_insert_chunk(uint32_t kaddr, uint32_t 
 #pragma unroll
   for (int k = 0; k < KC; ++k) {
     slb[k] = hash_key(key[k], log2cap) << 2;
-    old[k] = key[k];
-    if (active & (1u << k)) old[k] = atoms_cas(kaddr + slb[k], kEmptyKeyU, key[k]);
+    old[k] = atoms_cas_if((active >> k) & 1u, kaddr + slb[k], kEmptyKeyU, key[k], key[k]);
   }
 #pragma unroll
   for (int k = 0; k < KC; ++k) {
@@ -345,8 +359,7 @@ __device__ __forceinline__ uint32_t table_insert_chunk(uint32_t kaddr, uint32_t 
       }
   }
 #pragma unroll
-  for (int k = 0; k < KC; ++k)
-    if (active & (1u << k)) reds_add(kaddr + capb + slb[k], w[k]);
+  for (int k = 0; k < KC; ++k) reds_add_if((active >> k) & 1u, kaddr + capb + slb[k], w[k]);
   return fresh;
 }
 
