@@ -221,7 +221,8 @@ def bench_single(args):
                                                        ("udg", np.float64), ("cw", np.float64))}
     o_pin = pinned(o_h)
 
-    tb = {k: torch.from_numpy(v) for k, v in bufs.items()}  # same memory; torch's host ops are threaded
+    use_torch_host = os.environ.get("BENCH_E2E_HOST", "numpy") == "torch"
+    tb = {k: torch.from_numpy(v) for k, v in bufs.items()}  # same memory
     t_vdeg, t_iota = torch.from_numpy(vdeg), torch.arange(nv, dtype=torch.int64)
 
     def e2e_reset():
@@ -236,14 +237,18 @@ def bench_single(args):
         for _ in range(k):
             it += 1
             uploads += it == 1
-            tb["cw"].zero_()  # distCleanCWandCU, louvain.cpp:664
-            tb["usz"].zero_()
-            tb["udg"].zero_()
+            if use_torch_host:  # distCleanCWandCU, louvain.cpp:664
+                tb["cw"].zero_(), tb["usz"].zero_(), tb["udg"].zero_()
+            else:
+                bufs["cw"].fill(0), bufs["usz"].fill(0), bufs["udg"].fill(0)
             gpu_for_louvain_iteration(nv, o_pin, edges_p, bufs["curr"], bufs["target"], vdeg, bufs["csize"],
                                       bufs["cdeg"], bufs["usz"], bufs["udg"], {}, {}, {}, const, bufs["cw"], 0,
                                       it, gpu)
-            tb["csize"].add_(tb["usz"])  # distUpdateLocalCinfo, louvain.cpp:679
-            tb["cdeg"].add_(tb["udg"])
+            if use_torch_host:  # distUpdateLocalCinfo, louvain.cpp:679
+                tb["csize"].add_(tb["usz"]), tb["cdeg"].add_(tb["udg"])
+            else:
+                np.add(bufs["csize"], bufs["usz"], out=bufs["csize"])
+                np.add(bufs["cdeg"], bufs["udg"], out=bufs["cdeg"])
             le = gpu_reduce_mod(bufs["cdeg"], bufs["cw"], gpu, nv)
             q = le[0] * const - le[1] * const * const
             if q - prev < 1e-6:
@@ -271,6 +276,8 @@ def bench_single(args):
     # ---- CPU baseline beside it (bounded sample: phase 0 of the same graph) -----
     cpu = None
     try:
+        if args.no_cpu_baseline:
+            raise RuntimeError("skipped by --no-cpu-baseline")
         from oracle.binding import Oracle, Reference
         t_cpu = g.tails.cpu().numpy()
         w_cpu = g.weights.cpu().numpy()
@@ -323,6 +330,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuvite_b200", choices=["cuvite_b200", "reference"])
     ap.add_argument("--scale", type=int, default=None, help="override the R-MAT scale (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (debug)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -69,8 +69,10 @@ struct HostBuf {  // pinned staging
 // (localCupdate / remoteCupdate are ADDED to, louvain.cpp:2307-2376).
 template <typename F>
 static void host_parallel_for(int64_t n, F body) {
-  unsigned hw = std::thread::hardware_concurrency();
-  int nt = static_cast<int>(hw == 0 ? 4 : (hw > 16 ? 16 : hw));
+  static int nt = [] {
+    if (const char *s = getenv("CVB_HOST_THREADS")) return atoi(s) > 0 ? atoi(s) : 1;
+    return 1;  // measured on the B200 host: spawning helpers per call costs more than the 2M adds
+  }();
   if (n < (1 << 16) || nt <= 1) {
     body(0, n);
     return;
