@@ -101,6 +101,8 @@ class GpuGraph:
 
     def upload_device(self, offsets, tails, weights, base: int = 0, nv_global: int | None = None):
         """Device-resident CSR (torch CUDA tensors: int64, int64, float64)."""
+        import torch
+        torch.cuda.synchronize(offsets.device)  # the engine reads on its own stream: producers must be done
         nv = offsets.numel() - 1
         check(self._L.cvb_graph_upload_device(self._h, nv, base, nv if nv_global is None else nv_global,
                                               C.c_void_p(offsets.data_ptr()), C.c_void_p(tails.data_ptr()),

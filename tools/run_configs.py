@@ -1,0 +1,118 @@
+"""Run the BASELINE.json configurations that are not the bench line and record the outcome.
+
+  C3  R-MAT scale-22, 1 GPU, full multi-phase Louvain with coarsening to convergence,
+      per-level Q / iterations / sizes against the reference CPU path (oracle/_ref, or the C port)
+  C4' R-MAT scale-24 (~268 M undirected edges) on ONE GPU: phase-0 sweeps, kernel time, roofline
+  C5' power-law alpha=1.8 (scaled down to fit the time budget) phase 0 against the oracle
+
+Writes gpurun_out/configs.json (copied into profiles/ by hand).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cuvite_b200 import graphgen as gg  # noqa: E402
+from cuvite_b200.engine import GpuGraph, set_gpuDevices  # noqa: E402
+from oracle.binding import Oracle, Reference  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def main():
+    which = sys.argv[1:] or ["c3", "c4", "c5"]
+    set_gpuDevices(0)
+    out = {}
+    if "c3" in which:
+        scale = int(os.environ.get("C3_SCALE", "22"))
+        g = gg.rmat(scale, seed=2, device="cuda")
+        gpu = GpuGraph()
+        gpu.upload_device(g.offsets, g.tails, g.weights)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lq, li, ln, comm = gpu.run()
+        torch.cuda.synchronize()
+        t_gpu = time.perf_counter() - t0
+        o, t, w = g.offsets.cpu().numpy(), g.tails.cpu().numpy(), g.weights.cpu().numpy()
+        ref = Reference() if Reference.available() else Oracle()
+        t0 = time.perf_counter()
+        want = ref.run(o, t, w)
+        t_cpu = time.perf_counter() - t0
+        dq = [abs(a - b) for a, b in zip(lq, want.level_q)]
+        out["C3"] = {"workload": f"R-MAT scale-{scale}, full multi-phase Louvain, 1 GPU", "nv": g.nv, "csr_entries": g.ne,
+                     "levels": len(lq), "gpu_level_q": lq, "ref_level_q": list(want.level_q), "max_abs_dq": max(dq) if dq else 0.0,
+                     "level_iters_equal": li == list(want.level_iters), "level_nv_equal": ln == list(want.level_nv),
+                     "final_assignment_equal": bool(np.array_equal(comm, want.comm)),
+                     "gpu_seconds_total": t_gpu, "cpu_reference_seconds_total": t_cpu,
+                     "cpu_kind": type(ref).__name__, "cpu_threads": ref.num_threads()}
+        print(json.dumps(out["C3"]), flush=True)
+        gpu.close()
+        del g
+        torch.cuda.empty_cache()
+    if "c4" in which:
+        scale = int(os.environ.get("C4_SCALE", "24"))
+        g = gg.rmat(scale, seed=2, device="cuda")
+        nv, ne = g.nv, g.ne
+        gpu = GpuGraph()
+        gpu.upload_device(g.offsets, g.tails, g.weights)
+        del g
+        torch.cuda.empty_cache()
+        info = gpu.info()
+        gpu.phase_begin()
+        ms, qs, prev = [], [], -1.0
+        for it in range(8):
+            gpu.sweep()
+            sums = gpu.apply_and_reduce()
+            ms.append(gpu.last_sweep_ms())
+            q = gpu.modularity_from_sums(sums)
+            qs.append(q)
+            if q - prev < 1e-6:
+                break
+            prev = q
+            gpu.rotate_labels()
+        b = 12 * ne + 40 * nv
+        out["C4_one_gpu"] = {"workload": f"R-MAT scale-{scale} on ONE B200, phase-0 sweeps", "nv": nv, "csr_entries": ne,
+                             "sweep_kernel_ms": ms, "q_per_iteration": qs,
+                             "edges_per_s_first": (ne / 2) / (ms[0] * 1e-3), "edges_per_s_later": (ne / 2) / (np.mean(ms[1:]) * 1e-3) if len(ms) > 1 else None,
+                             "roofline_frac_first": b / (ms[0] * 1e-3) / 1e9 / peak(),
+                             "roofline_frac_later": b / (np.mean(ms[1:]) * 1e-3) / 1e9 / peak() if len(ms) > 1 else None,
+                             "max_degree": int(info.max_degree), "giant_vertices": int(info.class_count[16])}
+        print(json.dumps(out["C4_one_gpu"]), flush=True)
+        gpu.close()
+        torch.cuda.empty_cache()
+    if "c5" in which:
+        nv, m = 1 << 22, 1 << 26  # 4 M vertices, 64 M sampled edges (C5 is 2^25 / 512 M on 8 GPUs)
+        g = gg.power_law(nv, m, alpha=1.8, max_degree=1 << 20, seed=4, device="cuda")
+        gpu = GpuGraph()
+        gpu.upload_device(g.offsets, g.tails, g.weights)
+        info = gpu.info()
+        q, iters = gpu.phase_run()
+        cvect = gpu.labels(0)
+        o, t, w = g.offsets.cpu().numpy(), g.tails.cpu().numpy(), g.weights.cpu().numpy()
+        want = Oracle().phase(o, t, w)
+        gpu.phase_begin()
+        gpu.sweep()
+        gpu.sync()
+        ms1 = gpu.last_sweep_ms()
+        out["C5_scaled"] = {"workload": "power-law alpha=1.8, nv=2^22, 2^26 sampled edges, 1 GPU, phase 0", "nv": g.nv,
+                            "csr_entries": g.ne, "max_degree": int(info.max_degree), "giant_vertices": int(info.class_count[16]),
+                            "q_gpu": q, "q_ref": want.q, "iters_gpu": iters, "iters_ref": want.iters,
+                            "labels_equal": bool(np.array_equal(cvect, want.cvect)), "first_sweep_ms": ms1}
+        print(json.dumps(out["C5_scaled"]), flush=True)
+        gpu.close()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
