@@ -157,6 +157,7 @@ struct cvb_engine {
   DevBuf<uint32_t> big_meta;
   int64_t big_chunks = 0;
   int64_t giant_chunks = 0, giant_slots = 0;
+  bool use_tma = false;        // CVB_TMA=1: cp.async.bulk + mbarrier staging of tails/weights tiles
   bool use_cluster = false;    // CVB_CLUSTER=1: DSMEM cluster kernels for 8193..65536
   bool giant_direct = false;   // CVB_GIANT_DIRECT=1: giant entries go straight to the global tables
   bool use_first_sweep = true; // cvb env CVB_NO_FIRST_SWEEP=1 disables the singleton fast path
@@ -260,23 +261,29 @@ int launch_sweep(cvb_engine *e) {
   return CVB_OK;
 }
 
-template <int TPV, int KC, int NCH, int MINB>
-int launch_hash(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const vid_t *list, int64_t n) {
+template <int TPV, int KC, int NCH, int MINB, bool TMA>
+int launch_hash_impl(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const vid_t *list, int64_t n) {
   constexpr int VPB = TPV <= 32 ? 256 / TPV : 1;
   constexpr int THREADS = TPV <= 32 ? 256 : TPV;
-  const size_t smem = hash_block_smem<TPV, KC, NCH>();
+  const size_t smem = hash_block_smem<TPV, KC, NCH, TMA>();
   static bool configured = false;
   if (!configured) {
-    CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_hash<TPV, KC, NCH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
+    CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_hash<TPV, KC, NCH, MINB, TMA>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = true;
   }
   int64_t grid = (n + VPB - 1) / VPB;
   const int64_t cap = static_cast<int64_t>(e->num_sms) * MINB;
   if (grid > cap) grid = cap;
-  k_sweep_u32_hash<TPV, KC, NCH, MINB><<<static_cast<int>(grid), THREADS, smem, st>>>(p, list, static_cast<int>(n));
+  k_sweep_u32_hash<TPV, KC, NCH, MINB, TMA><<<static_cast<int>(grid), THREADS, smem, st>>>(p, list, static_cast<int>(n));
   e->launches++;
   return CVB_OK;
+}
+
+template <int TPV, int KC, int NCH, int MINB>
+int launch_hash(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const vid_t *list, int64_t n) {
+  if (TPV >= 128 && e->use_tma) return launch_hash_impl<TPV, KC, NCH, MINB, (TPV >= 128)>(e, st, p, list, n);
+  return launch_hash_impl<TPV, KC, NCH, MINB, false>(e, st, p, list, n);
 }
 
 template <int CS>
@@ -681,6 +688,7 @@ cvb_engine *cvb_create(void *stream) {
   if (const char *s = getenv("CVB_NO_FIRST_SWEEP")) e->use_first_sweep = !(s[0] == '1');
   if (const char *s = getenv("CVB_GIANT_DIRECT")) e->giant_direct = (s[0] == '1');
   if (const char *s = getenv("CVB_CLUSTER")) e->use_cluster = (s[0] == '1');
+  if (const char *s = getenv("CVB_TMA")) e->use_tma = (s[0] == '1');
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) e->num_sms = sms;
   if (stream) {

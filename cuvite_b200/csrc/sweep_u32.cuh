@@ -212,10 +212,13 @@ __global__ void __launch_bounds__(256) k_sweep_u32_group(SweepU32Params p, const
 // Per table: keys[CAP] wts[CAP] (uint32), meta[4] = {-, selfloop, counter0, -}.
 // ---------------------------------------------------------------------------
 // dynamic shared memory of one block of k_sweep_u32_hash<TPV, KC, NCH>
-template <int TPV, int KC, int NCH>
+// TPV >= 128 (one block per vertex) also stages the vertex's tails and weights tile
+// (KC*NCH*TPV + 4 entries each, filled by TMA) and one mbarrier.
+template <int TPV, int KC, int NCH, bool TMA = false>
 __host__ __device__ constexpr size_t hash_block_smem() {
   return (TPV <= 32) ? static_cast<size_t>(256 / TPV) * (2 * KC * NCH * TPV) * 8
-                     : static_cast<size_t>(2 * KC * NCH * TPV) * 8 + 16;
+                     : static_cast<size_t>(2 * KC * NCH * TPV) * 8 + 16 +
+                           (TMA ? 2 * static_cast<size_t>(KC * NCH * TPV + 4) * 4 + 16 : 0);
 }
 
 template <int TPV>
@@ -285,6 +288,28 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+
+// ---- TMA (bulk async copy) + mbarrier: stage a vertex's tails / weights tile in shared memory ----
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on the mbarrier (UBLKCP in SASS).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Second hash for double hashing: an odd step, so every slot of the
 // power-of-two table is reachable.
@@ -385,7 +410,13 @@ __device__ __forceinline__ VertexHeader fetch_header(const SweepU32Params &p, vi
 // vertex are contiguous; every collective carries the vertex's lane mask), so
 // the per-vertex bookkeeping instructions are issued once for several
 // vertices; TPV >= 64: one block per vertex.
-template <int TPV, int KC, int NCH, int MINB>
+// TMA = true (block-per-vertex classes, CVB_TMA=1): the tails / weights tile of the next
+// vertex is brought into shared memory by two cp.async.bulk copies signalled on an mbarrier
+// while the current vertex is evaluated, and the insert phase reads it with LDS.  Measured on
+// B200 (scale-20) this single-stage staging is ~10 % SLOWER than per-thread streaming loads
+// (the copy is issued only after the previous tile is consumed, and the tile costs occupancy),
+// so it is off by default; see DESIGN.md.
+template <int TPV, int KC, int NCH, int MINB, bool TMA = false>
 __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
     k_sweep_u32_hash(SweepU32Params p, const vid_t *__restrict__ list, int n) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
@@ -407,12 +438,23 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
   uint32_t *wts = keys + CAP;
   uint32_t *meta = keys + 2 * CAP;  // only for TPV > 32
   const uint32_t kaddr = smem_addr(keys);
+  // TMA-staged tile of the current vertex (block-per-vertex classes)
+  constexpr bool kTma = TMA && TPV >= 128;
+  constexpr int kTileWords = K * TPV + 4;  // +4: the row start is only 4-byte aligned, copies are 16-byte aligned
+  uint32_t *tile_tails = meta + 4;
+  uint32_t *tile_weights = tile_tails + kTileWords;
+  const uint32_t mbar = smem_addr(tile_weights + kTileWords);
+  uint32_t tile_parity = 0u;
   for (int s = tid; s < CAP; s += TPV) {
     keys[s] = kEmptyKeyU;
     wts[s] = 0u;
   }
   if (TPV > 32) {
     if (tid < 4) meta[tid] = 0u;
+    if (kTma && tid == 0) {
+      mbar_init(mbar, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
   } else {
     __syncwarp(gmask);
@@ -426,6 +468,16 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
   // while vertex i is processed
   VertexHeader hc = fetch_header(p, list[item]);
   vid_t v_next = (item + stride < n) ? list[item + stride] : -1;
+  // stage the tails/weights of [e0, e1): one elected thread arms the mbarrier and issues two bulk copies
+  auto issue_tile = [&](eid_t e0, eid_t e1) {
+    const eid_t a0 = e0 & ~static_cast<eid_t>(3);
+    const uint32_t bytes = static_cast<uint32_t>(((e1 - a0) * 4 + 15) & ~static_cast<eid_t>(15));
+    fence_proxy_async();  // generic-proxy reads of the previous tile are ordered before the async refill
+    mbar_expect_tx(mbar, 2u * bytes);
+    tma_load_1d(smem_addr(tile_tails), p.tails + a0, bytes, mbar);
+    tma_load_1d(smem_addr(tile_weights), p.weights + a0, bytes, mbar);
+  };
+  if (kTma && tid == 0) issue_tile(hc.e0, hc.e1);
   for (; item < n; item += stride) {
     VertexHeader hn = hc;
     if (v_next >= 0) hn = fetch_header(p, v_next);
@@ -444,6 +496,11 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
 
     const vid_t *__restrict__ row_tails = p.tails + e0;
     const uint32_t *__restrict__ row_weights = p.weights + e0;
+    const int tile_off = static_cast<int>(e0 & 3);
+    if (kTma) {
+      mbar_wait(mbar, tile_parity);  // the tile of this vertex has landed
+      tile_parity ^= 1u;
+    }
     // claims of this lane: key, community degree and slot of every entry that
     // opened a new table slot (valid where the fresh bit is set)
     uint32_t ckey[K], cay[K];
@@ -461,8 +518,13 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
           tail[k] = self;  // a safe address for the gather of idle lanes
           w[k] = 0u;
           if (i < deg) {
-            tail[k] = __ldcs(&row_tails[i]);
-            w[k] = __ldcs(&row_weights[i]);
+            if (kTma) {
+              tail[k] = static_cast<vid_t>(tile_tails[tile_off + i]);
+              w[k] = tile_weights[tile_off + i];
+            } else {
+              tail[k] = __ldcs(&row_tails[i]);
+              w[k] = __ldcs(&row_weights[i]);
+            }
             validm |= 1u << k;
           }
         }
@@ -501,6 +563,9 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
       __syncthreads();
       c0u = meta[2];
       slu = meta[1];
+      // every thread has consumed this vertex's tile: refill it for the next vertex while
+      // this one is evaluated and committed
+      if (kTma && tid == 0 && v_next >= 0) issue_tile(hn.e0, hn.e1);
     } else {
       __syncwarp(gmask);
     }

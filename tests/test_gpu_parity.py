@@ -280,6 +280,23 @@ def test_reference_main_runs_on_our_plugin(tmp_path):
     assert outs["cpu"][1] == outs["gpu"][1]
 
 
+def test_tma_staged_variant_matches_reference(monkeypatch):
+    """CVB_TMA=1: block-per-vertex classes read their tails/weights tile from a cp.async.bulk +
+    mbarrier staged shared-memory buffer; same results as the golden fixture."""
+    from cuvite_b200.engine import GpuGraph
+    monkeypatch.setenv("CVB_TMA", "1")
+    gpu = GpuGraph()
+    g = load_golden("hub30k")  # has vertices in the 513..8192 block classes
+    gpu.upload(*_csr(g))
+    gpu.phase_begin()
+    for k in range(int(g["iters"])):
+        gpu.sweep()
+        assert np.array_equal(gpu.labels(2), g["targets"][k])
+        gpu.apply_and_reduce()
+        gpu.rotate_labels()
+    gpu.close()
+
+
 @pytest.mark.parametrize("cluster", [False, True])
 def test_true_giant_hub_matches_oracle(oracle, cluster, monkeypatch):
     """Vertices above 8192 entries: global-table path (default) and the thread-block-cluster /
