@@ -873,7 +873,13 @@ static int apply_reduce_zero_deltas(cvb_engine *e) {
     CVB_CUDA(cudaMemsetAsync(e->dsize.p, 0, e->nvg * sizeof(int32_t), st));
     e->labels_only = true;
   }
-  return apply_reduce_async(e);
+  const int grid = grid_for(e->nvl, kReduceBlock, e->num_sms * 4);
+  k_reduce_only<<<grid, kReduceBlock, 0, st>>>(e->base, e->base + e->nvl, e->nvl, e->cdeg.p, e->cw.p, e->partials.p,
+                                               e->ticket.p, e->d_sums.p);
+  e->launches++;
+  CVB_CUDA(cudaGetLastError());
+  CVB_CUDA(cudaMemcpyAsync(e->h_sums.p, e->d_sums.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  return CVB_OK;
 }
 
 int cvb_apply_and_reduce(cvb_engine *e, double sums[2]) {

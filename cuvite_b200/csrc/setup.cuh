@@ -365,6 +365,77 @@ __global__ void k_apply_label_diff(int64_t nv_global, const vid_t *__restrict__ 
   }
 }
 
+// Reduction only (labels-only exchange: the deltas were applied from the label diff):
+// a2 over the owned communities, e over the local vertices; same two-level scheme.
+__global__ void __launch_bounds__(kReduceBlock) k_reduce_only(int64_t own0, int64_t own1, int64_t nv_local,
+                                                             const double *__restrict__ cdeg,
+                                                             const double *__restrict__ cw,
+                                                             double *__restrict__ partials,
+                                                             unsigned int *__restrict__ ticket,
+                                                             double *__restrict__ out) {
+  __shared__ double sh_e[kReduceBlock / 32], sh_a[kReduceBlock / 32];
+  __shared__ bool last;
+  double e = 0.0, a2 = 0.0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t t0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (int64_t c = own0 + t0; c < own1; c += stride) {
+    const double d = cdeg[c];
+    a2 += d * d;
+  }
+  for (int64_t i = t0; i < nv_local; i += stride) e += cw[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh_e[threadIdx.x >> 5] = e;
+    sh_a[threadIdx.x >> 5] = a2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double be = 0.0, ba = 0.0;
+    for (int w = 0; w < kReduceBlock / 32; ++w) {
+      be += sh_e[w];
+      ba += sh_a[w];
+    }
+    partials[2 * blockIdx.x] = be;
+    partials[2 * blockIdx.x + 1] = ba;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double te = 0.0, ta = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kReduceBlock) {
+      te += __ldcg(&partials[2 * b]);
+      ta += __ldcg(&partials[2 * b + 1]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      te += __shfl_xor_sync(0xffffffffu, te, o);
+      ta += __shfl_xor_sync(0xffffffffu, ta, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      sh_e[threadIdx.x >> 5] = te;
+      sh_a[threadIdx.x >> 5] = ta;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double fe = 0.0, fa = 0.0;
+      for (int w = 0; w < kReduceBlock / 32; ++w) {
+        fe += sh_e[w];
+        fa += sh_a[w];
+      }
+      out[0] = fe;
+      out[1] = fa;
+      *ticket = 0;
+    }
+  }
+}
+
 // ---- boundary-call helpers ---------------------------------------------------
 __global__ void k_scatter_labels(int64_t n, const int64_t *__restrict__ idx, const int64_t *__restrict__ val,
                                  vid_t *__restrict__ dst) {
