@@ -101,8 +101,10 @@ def run_reference(args):
         return
     import numpy as np
     from oracle.binding import Oracle, Reference
+    import torch
     scale = BASE_SCALE + (args.gpus - 1).bit_length() if args.scale is None else args.scale
-    g = make_graph(scale, "cpu", args.gpus > 1)
+    # same deterministic generator on either device; the GPU only builds the input faster
+    g = make_graph(scale, "cuda" if torch.cuda.is_available() else "cpu", args.gpus > 1).cpu()
     o, t, w = g.offsets.numpy(), g.tails.numpy(), g.weights.numpy()
     if Reference.available():
         impl, kind = Reference(), "reference"
