@@ -6,6 +6,10 @@
 # from the sources where they lie under $REF (default /root/reference) into
 #     oracle/_ref/libcuvite_ref.so   (ref_harness.cpp C entry points)
 #     oracle/_ref/gc_cpu64           (the reference CLI, 64-bit ids / double)
+#     oracle/_ref/gc_gpu64           (the reference CLI with ITS OWN CUDA path — louvain_cuda.cu,
+#                                     modularity.cu, GpuGraph.cu — recompiled for sm_100 with
+#                                     -DPRINT_TIMEDS: the "recompiled kernels" baseline that
+#                                     tools/ref_cuda_baseline.py times on the B200 box)
 # Only binaries land in oracle/_ref/ (git-ignored, NOT gpurun-ignored).  The
 # three mechanical accommodations SURVEY.md §8c lists are applied to a scratch
 # copy under a temp dir, never to the repo:
@@ -52,5 +56,18 @@ if [ -f "$REPO/cuvite_b200/libcuvite_b200.so" ]; then
        -L"$REPO/cuvite_b200" -lcuvite_b200 -Wl,-rpath,'$ORIGIN/../../cuvite_b200' \
        -Wl,-rpath,/usr/local/cuda/lib64 -o "$OUT/gc_gpu_dropin"
   echo "built $OUT/gc_gpu_dropin"
+fi
+# the reference's own CUDA path, recompiled for Blackwell (baseline only; SURVEY.md §8c "also compilable")
+if command -v nvcc >/dev/null 2>&1; then
+  for f in louvain_cuda.cu modularity.cu GpuGraph.cu GpuGraph.cuh louvain_cuda.cuh louvain_cuda_constants.cuh \
+           louvain_cuda_cpp_interface.hpp; do
+    sed 's/default(none)/default(shared)/g' "$REF/$f" > "$TMP/$f"
+  done
+  nvcc -ccbin "$CXX" -std=c++14 -O3 -gencode arch=compute_100,code=sm_100 -w \
+       -Xcompiler -fopenmp,-fpermissive,-w -DRUNONGPU=1 -DPRINT_TIMEDS -DDONT_CREATE_DIAG_FILES \
+       -I"$HERE/mpi_shim" -I"$TMP" \
+       "$TMP"/{main,coloring,compare,distgraph,louvain,rebuild,utils}.cpp \
+       "$TMP"/{louvain_cuda,modularity,GpuGraph}.cu -lcudart -lgomp -o "$OUT/gc_gpu64"
+  echo "built $OUT/gc_gpu64"
 fi
 echo "built $OUT/gc_cpu64 $OUT/libcuvite_ref.so"
