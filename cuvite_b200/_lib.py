@@ -52,6 +52,9 @@ SIGNATURES = {
                                      _i64, _vp, _vp, _vp, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cvb_reduce_mod": (_i32, [_vp, _i64, _vp, _vp, C.POINTER(_f64)]),
     "cvb_coarsen": (_i32, [_vp, C.POINTER(_i64)]),
+    "cvb_renumber": (_i32, [_vp, _vp, _i64, _vp, C.POINTER(_i64)]),
+    "cvb_contract_local": (_i32, [_vp, _vp, _i64, C.POINTER(_i64)]),
+    "cvb_graph_from_pairs": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i64]),
     "cvb_graph_download": (_i32, [_vp, _vp, _vp, _vp]),
     "cvb_louvain_run": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "cvb_launch_count": (_i64, [_vp]),

@@ -61,12 +61,13 @@ __global__ void k_iota_i32(int32_t *p, int64_t n) {
 }
 
 // One warp per row: key[e] = (vnew[row] << 32) | vnew[tail[e]]
+// (vnew is indexed by GLOBAL vertex id; row r of this engine is vertex base + r)
 __global__ void k_edge_keys(const eid_t *__restrict__ offsets, const vid_t *__restrict__ tails,
-                            const int32_t *__restrict__ vnew, int64_t nv, uint64_t *__restrict__ keys) {
+                            const int32_t *__restrict__ vnew, int64_t base, int64_t nv, uint64_t *__restrict__ keys) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31u;
   if (row >= nv) return;
-  const uint64_t hi = static_cast<uint64_t>(static_cast<uint32_t>(vnew[row])) << 32;
+  const uint64_t hi = static_cast<uint64_t>(static_cast<uint32_t>(vnew[base + row])) << 32;
   for (eid_t e = offsets[row] + lane; e < offsets[row + 1]; e += 32)
     keys[e] = hi | static_cast<uint32_t>(vnew[tails[e]]);
 }
@@ -79,18 +80,33 @@ __global__ void k_heads(const uint64_t *__restrict__ keys, int64_t ne, int32_t *
 }
 
 // seg[e] = inclusive-scan(head)[e] - 1 is the merged entry of sorted entry e.
-// Emits tails, per-row counts and the start of each merged entry.
-__global__ void k_emit_entries(const uint64_t *__restrict__ keys, const int32_t *__restrict__ head,
-                               const int32_t *__restrict__ seg_incl, int64_t ne, vid_t *__restrict__ ntails,
-                               int64_t *__restrict__ seg_start, unsigned long long *__restrict__ row_count) {
+// Emits the distinct keys and the start of each merged entry.
+__global__ void k_emit_pairs(const uint64_t *__restrict__ keys, const int32_t *__restrict__ head,
+                             const int32_t *__restrict__ seg_incl, int64_t ne, uint64_t *__restrict__ ukeys,
+                             int64_t *__restrict__ seg_start) {
   for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < ne;
        e += static_cast<int64_t>(gridDim.x) * blockDim.x)
     if (head[e]) {
       const int32_t s = seg_incl[e] - 1;
-      ntails[s] = static_cast<vid_t>(keys[e] & 0xFFFFFFFFull);
+      ukeys[s] = keys[e];
       seg_start[s] = e;
-      atomicAdd(&row_count[keys[e] >> 32], 1ull);
     }
+}
+
+// Distinct ascending pairs -> CSR pieces: tails[s] = dst, row_count[src - base]++.
+// A source outside [base, base + nv_local) raises *bad (the caller routed a pair wrongly).
+__global__ void k_pairs_to_rows(const uint64_t *__restrict__ ukeys, int64_t m, int64_t base, int64_t nv_local,
+                                vid_t *__restrict__ ntails, unsigned long long *__restrict__ row_count,
+                                int *__restrict__ bad) {
+  for (int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; s < m;
+       s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = static_cast<int64_t>(ukeys[s] >> 32) - base;
+    ntails[s] = static_cast<vid_t>(ukeys[s] & 0xFFFFFFFFull);
+    if (row < 0 || row >= nv_local)
+      *bad = 1;
+    else
+      atomicAdd(&row_count[row], 1ull);
+  }
 }
 
 // Weight of merged entry s = sum of the sorted weights in [seg_start[s], seg_start[s+1])

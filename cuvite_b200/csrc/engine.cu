@@ -157,6 +157,16 @@ struct cvb_engine {
   DevBuf<uint32_t> big_meta;
   int64_t big_chunks = 0;
   int64_t giant_chunks = 0, giant_slots = 0;
+  // coarsening stage 2 output: distinct (src << 32 | dst) pairs of the local rows, ascending
+  DevBuf<uint64_t> pair_keys;
+  DevBuf<unsigned char> pair_w;
+  int64_t pair_count = 0;
+  // The global tables of the big vertices are processed in batches that share ONE arena small
+  // enough to stay L2-resident (insert -> eval -> next batch reuses the same lines), instead of
+  // one table per vertex spread over gigabytes of HBM.
+  struct GiantBatch { int64_t chunk_lo, chunk_hi, piece_lo, piece_hi, slot_base; };
+  std::vector<GiantBatch> giant_batches;
+  int64_t giant_arena_slots = 4 << 20;  // 32 MB of 8-byte slots; CVB_GIANT_ARENA_MB overrides
   bool use_tma = false;        // CVB_TMA=1: cp.async.bulk + mbarrier staging of tails/weights tiles
   bool use_cluster = false;    // CVB_CLUSTER=1: DSMEM cluster kernels for 8193..65536
   bool giant_direct = false;   // CVB_GIANT_DIRECT=1: giant entries go straight to the global tables
@@ -396,7 +406,7 @@ int launch_sweep_u32(cvb_engine *e) {
     if ((n = cnt(kClsC2)) > 0) CVB_TRY(launch_cluster<2>(e, e->aux[1], p, lst(kClsC2), n));
   }
   if ((n = e->class_start[kClsGiant + 1] - e->class_start[gcls]) > 0) {
-    GiantTables gt;
+    GiantTables gt{};
     gt.chunk_owner = e->gchunk_owner.p;
     gt.chunk_start = e->giant_layout.p;
     gt.table_start = e->giant_layout.p + (n + 1);
@@ -404,27 +414,32 @@ int launch_sweep_u32(cvb_engine *e) {
     gt.gmeta = e->gmeta.p;
     gt.piece_gain = e->gpiece_gain.p;
     gt.piece_key = e->gpiece_key.p;
-    const int64_t pieces = e->giant_slots / kGiantPiece;
-    int64_t g1 = e->giant_chunks < 2LL * e->num_sms ? e->giant_chunks : 2LL * e->num_sms;
     constexpr int kGiantSmem = 2 * kGiantChunk * 8;
     static bool giant_configured = false;
     if (!giant_configured) {
       CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_giant_insert, cudaFuncAttributeMaxDynamicSharedMemorySize, kGiantSmem));
       giant_configured = true;
     }
-    if (e->giant_direct) {
-      int64_t g0 = e->giant_chunks < 4LL * e->num_sms ? e->giant_chunks : 4LL * e->num_sms;
-      k_sweep_u32_giant_insert_direct<<<static_cast<int>(g0), 512, 0, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
-                                                                                  e->giant_chunks);
-    } else {
-      k_sweep_u32_giant_insert<<<static_cast<int>(g1), 512, kGiantSmem, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
-                                                                                    e->giant_chunks);
+    for (const auto &b : e->giant_batches) {
+      gt.slot_base = b.slot_base;
+      const int64_t nch = b.chunk_hi - b.chunk_lo, npc = b.piece_hi - b.piece_lo;
+      if (e->giant_direct) {
+        const int64_t g0 = nch < 4LL * e->num_sms ? nch : 4LL * e->num_sms;
+        k_sweep_u32_giant_insert_direct<<<static_cast<int>(g0), 512, 0, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
+                                                                                    b.chunk_lo, b.chunk_hi);
+      } else {
+        const int64_t g1 = nch < 2LL * e->num_sms ? nch : 2LL * e->num_sms;
+        k_sweep_u32_giant_insert<<<static_cast<int>(g1), 512, kGiantSmem, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
+                                                                                      b.chunk_lo, b.chunk_hi);
+      }
+      const int64_t g2 = npc < 4LL * e->num_sms ? npc : 4LL * e->num_sms;
+      k_sweep_u32_giant_eval<<<static_cast<int>(g2), 512, 0, e->aux[1]>>>(p, lst(gcls), (int)n, gt, b.piece_lo,
+                                                                         b.piece_hi);
+      e->launches += 2;
     }
-    int64_t g2 = pieces < 4LL * e->num_sms ? pieces : 4LL * e->num_sms;
-    k_sweep_u32_giant_eval<<<static_cast<int>(g2), 512, 0, e->aux[1]>>>(p, lst(gcls), (int)n, gt, pieces);
     k_sweep_u32_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(p, lst(gcls), (int)n,
                                                                                          gt);
-    e->launches += 3;
+    e->launches += 1;
   }
   // stream 2: warp-level and sub-warp hash classes
   if ((n = cnt(kClsH1K)) > 0) CVB_TRY((launch_hash<64, 4, 2, 16>(e, e->aux[2], p, lst(kClsH1K), n)));
@@ -569,21 +584,30 @@ int post_graph(cvb_engine *e) {
       k_giant_layout<<<1, 32, 0, st>>>(e->offsets.p, e->list.p + e->class_start[gcls], (int)ngiant,
                                        e->giant_layout.p, e->giant_layout.p + (ngiant + 1));
       e->launches++;
-      int64_t tot[2];
-      CVB_CUDA(cudaMemcpyAsync(&tot[0], e->giant_layout.p + ngiant, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-      CVB_CUDA(cudaMemcpyAsync(&tot[1], e->giant_layout.p + (ngiant + 1) + ngiant, sizeof(int64_t),
-                               cudaMemcpyDeviceToHost, st));
+      std::vector<int64_t> lay(2 * (ngiant + 1));
+      CVB_CUDA(cudaMemcpyAsync(lay.data(), e->giant_layout.p, lay.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
       CVB_CUDA(cudaStreamSynchronize(st));
-      e->giant_chunks = tot[0];
-      e->giant_slots = tot[1];
-      CVB_TRY(e->gslots.ensure(e->giant_slots));
+      const int64_t *cs = lay.data(), *ts = lay.data() + (ngiant + 1);
+      e->giant_chunks = cs[ngiant];
+      e->giant_slots = ts[ngiant];
+      // batches of consecutive big vertices whose tables fit the arena together
+      e->giant_batches.clear();
+      int64_t arena = 0;
+      for (int64_t i = 0; i < ngiant;) {
+        int64_t j = i + 1;
+        while (j < ngiant && ts[j + 1] - ts[i] <= e->giant_arena_slots) ++j;
+        e->giant_batches.push_back({cs[i], cs[j], ts[i] / kGiantPiece, ts[j] / kGiantPiece, ts[i]});
+        if (ts[j] - ts[i] > arena) arena = ts[j] - ts[i];
+        i = j;
+      }
+      CVB_TRY(e->gslots.ensure(arena));
       CVB_TRY(e->gmeta.ensure(3 * ngiant + 4));
       CVB_TRY(e->gpiece_gain.ensure(e->giant_slots / kGiantPiece + 1));
       CVB_TRY(e->gpiece_key.ensure(e->giant_slots / kGiantPiece + 1));
       CVB_TRY(e->gchunk_owner.ensure(e->giant_chunks + 1));
       k_giant_chunk_owner<<<static_cast<int>(ngiant), 64, 0, st>>>(e->giant_layout.p, (int)ngiant, e->gchunk_owner.p);
       e->launches++;
-      k_giant_init_slots<<<grid_for(e->giant_slots, 256), 256, 0, st>>>(e->gslots.p, e->giant_slots);
+      k_giant_init_slots<<<grid_for(arena, 256), 256, 0, st>>>(e->gslots.p, arena);
       e->launches++;
       CVB_CUDA(cudaMemsetAsync(e->gmeta.p, 0, (3 * ngiant + 4) * sizeof(uint32_t), st));
     }
@@ -687,6 +711,10 @@ cvb_engine *cvb_create(void *stream) {
   e->device = dev;
   if (const char *s = getenv("CVB_NO_FIRST_SWEEP")) e->use_first_sweep = !(s[0] == '1');
   if (const char *s = getenv("CVB_GIANT_DIRECT")) e->giant_direct = (s[0] == '1');
+  if (const char *s = getenv("CVB_GIANT_ARENA_MB")) {
+    const long mb = atol(s);
+    if (mb > 0) e->giant_arena_slots = static_cast<int64_t>(mb) << 17;
+  }
   if (const char *s = getenv("CVB_CLUSTER")) e->use_cluster = (s[0] == '1');
   if (const char *s = getenv("CVB_TMA")) e->use_tma = (s[0] == '1');
   int sms = 0;
@@ -729,7 +757,7 @@ void cvb_destroy(cvb_engine *e) {
   e->d_class_start.release(); e->d_class_entries.release();
   e->partials.release(); e->d_sums.release(); e->ticket.release(); e->d_flags.release();
   e->h_sums.release(); e->staging.release(); e->staging2.release(); e->giant.release(); e->h_stage.release();
-  e->packed.release(); e->giant_layout.release(); e->gslots.release();
+  e->packed.release(); e->giant_layout.release(); e->gslots.release(); e->pair_keys.release(); e->pair_w.release();
   e->gmeta.release(); e->gpiece_key.release(); e->gpiece_gain.release(); e->gchunk_gain.release();
   e->gchunk_key.release(); e->gchunk_owner.release(); e->big_layout.release(); e->big_owner.release();
   e->big_meta.release();
@@ -1009,6 +1037,8 @@ void *cvb_buffer(cvb_engine *e, int which) {
     case CVB_BUF_OFFSETS: return e->offsets.p;
     case CVB_BUF_TAILS: return e->tails.p;
     case CVB_BUF_WEIGHTS: return e->weights.p;
+    case CVB_BUF_PAIR_KEYS: return e->pair_keys.p;
+    case CVB_BUF_PAIR_WEIGHTS: return e->pair_w.p;
     default: return nullptr;
   }
 }
@@ -1166,123 +1196,211 @@ int cvb_reduce_mod(cvb_engine *e, int64_t nv, const double *local_cdeg, const do
 }
 
 // ---- coarsening + multi-phase driver -------------------------------------------
-static int coarsen_impl(cvb_engine *e, int64_t *new_nv_out, int32_t *d_compose, int64_t n_compose) {
-  CVB_CHECK(e && e->phase_ready, CVB_ERR_STATE, "cvb_coarsen: run a phase first");
-  CVB_CHECK(e->nvl == e->nvg, CVB_ERR_STATE, "cvb_coarsen is the one-GPU path");
-  CVB_CHECK(e->ne < 2147483000LL, CVB_ERR_CAPACITY, "cvb_coarsen: more than 2^31 entries on one GPU");
+// ---- coarsening in three stages (one rank runs them back to back; N ranks exchange the
+// ---- contracted pairs between stage 2 and stage 3, cuvite_b200/dist.py) --------------
+
+// Stage 1 — distReNumber (rebuild.cpp:72-85): vnew[i] = rank, in order of first appearance
+// scanning i ascending, of labels[i]'s community.  labels are ids in [0, n).
+static int renumber_impl(cvb_engine *e, const vid_t *labels, int64_t n, int32_t *vnew, int64_t *nnv_out) {
   cudaStream_t st = e->stream;
-  const int64_t nv = e->nvl, ne = e->ne;
-  const vid_t *cvect = e->lab[e->past].p;  // cvect = pastComm, louvain.cpp:741
+  DevBuf<int32_t> first, flag, rank;
+  DevBuf<unsigned char> tmp;
+  auto release = [&]() { first.release(); flag.release(); rank.release(); tmp.release(); };
+  struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
+  *nnv_out = 0;
+  if (n == 0) return CVB_OK;
+  CVB_TRY(first.ensure(n + 1)); CVB_TRY(flag.ensure(n + 1)); CVB_TRY(rank.ensure(n + 2));
+  k_fill_i32<<<grid_for(n, 256), 256, 0, st>>>(first.p, n, 0x7FFFFFFF);
+  k_first_appearance<<<grid_for(n, 256), 256, 0, st>>>(labels, n, first.p);
+  k_flag_first<<<grid_for(n, 256), 256, 0, st>>>(labels, first.p, n, flag.p);
+  size_t tb = 0;
+  CVB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.p, rank.p, static_cast<int>(n), st));
+  CVB_TRY(tmp.ensure(tb + 1024));
+  size_t tcap = tmp.cap;
+  CVB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tcap, flag.p, rank.p, static_cast<int>(n), st));
+  k_vertex_newid<<<grid_for(n, 256), 256, 0, st>>>(labels, first.p, rank.p, n, vnew);
+  e->launches += 5;
+  int32_t last_rank = 0, last_flag = 0;
+  CVB_CUDA(cudaMemcpyAsync(&last_rank, rank.p + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CVB_CUDA(cudaMemcpyAsync(&last_flag, flag.p + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CVB_CUDA(cudaStreamSynchronize(st));
+  *nnv_out = static_cast<int64_t>(last_rank) + last_flag;
+  return CVB_OK;
+}
+
+// Sort (key, weight) pairs by key (stable) and merge equal keys: ukeys / uw get the distinct
+// keys ascending and their summed weights (F64: summed sequentially in sorted order — the
+// reference's order on one rank; U32: exact in any order).
+static int sort_reduce_pairs(cvb_engine *e, const uint64_t *k_in, const void *w_in, int64_t m, int bits,
+                             DevBuf<uint64_t> &ukeys, DevBuf<unsigned char> &uw, int64_t *mu_out) {
+  cudaStream_t st = e->stream;
   const bool u32 = e->mode == CVB_WEIGHTS_U32;
   const size_t wbytes = u32 ? 4 : 8;
-  DevBuf<int32_t> first, flag, rank, vnew, head, seg;
-  DevBuf<uint64_t> k_in, k_out;
-  DevBuf<unsigned char> w_out, tmp, nw;
-  DevBuf<int64_t> seg_start, noff;
-  DevBuf<unsigned long long> row_count;
-  DevBuf<vid_t> ntails;
-  auto release = [&]() {
-    first.release(); flag.release(); rank.release(); vnew.release(); head.release(); seg.release();
-    k_in.release(); k_out.release(); w_out.release(); tmp.release(); nw.release(); seg_start.release();
-    noff.release(); row_count.release(); ntails.release();
-  };
+  *mu_out = 0;
+  if (m == 0) return CVB_OK;
+  CVB_CHECK(m < 2147483000LL, CVB_ERR_CAPACITY, "coarsening: more than 2^31 entries on one GPU");
+  DevBuf<uint64_t> k_out;
+  DevBuf<unsigned char> w_out, tmp;
+  DevBuf<int32_t> head, seg;
+  DevBuf<int64_t> seg_start;
+  auto release = [&]() { k_out.release(); w_out.release(); tmp.release(); head.release(); seg.release(); seg_start.release(); };
   struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
-  CVB_TRY(first.ensure(nv + 1)); CVB_TRY(flag.ensure(nv + 1)); CVB_TRY(rank.ensure(nv + 2));
-  CVB_TRY(vnew.ensure(nv + 1));
-  // distReNumber: first-appearance numbering
-  k_fill_i32<<<grid_for(nv, 256), 256, 0, st>>>(first.p, nv, 0x7FFFFFFF);
-  k_first_appearance<<<grid_for(nv, 256), 256, 0, st>>>(cvect, nv, first.p);
-  k_flag_first<<<grid_for(nv, 256), 256, 0, st>>>(cvect, first.p, nv, flag.p);
-  e->launches += 3;
-  size_t tb = 0;
-  CVB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.p, rank.p, static_cast<int>(nv), st));
-  size_t tb2 = 0, tb3 = 0, tb4 = 0;
-  if (ne > 0) {
+  size_t tb2 = 0, tb4 = 0;
+  if (u32)
     CVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb2, (uint64_t *)nullptr, (uint64_t *)nullptr,
-                                             (uint32_t *)nullptr, (uint32_t *)nullptr, static_cast<int>(ne), 0, 64, st));
-    CVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb3, (uint64_t *)nullptr, (uint64_t *)nullptr,
-                                             (double *)nullptr, (double *)nullptr, static_cast<int>(ne), 0, 64, st));
-    CVB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb4, (int32_t *)nullptr, (int32_t *)nullptr,
-                                           static_cast<int>(ne), st));
-  }
-  size_t tbytes = tb;
-  for (size_t x : {tb2, tb3, tb4}) tbytes = x > tbytes ? x : tbytes;
-  CVB_TRY(tmp.ensure(tbytes + 1024));
+                                             (uint32_t *)nullptr, (uint32_t *)nullptr, static_cast<int>(m), 0, 64, st));
+  else
+    CVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb2, (uint64_t *)nullptr, (uint64_t *)nullptr,
+                                             (double *)nullptr, (double *)nullptr, static_cast<int>(m), 0, 64, st));
+  CVB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb4, (int32_t *)nullptr, (int32_t *)nullptr, static_cast<int>(m), st));
+  CVB_TRY(tmp.ensure((tb2 > tb4 ? tb2 : tb4) + 1024));
+  CVB_TRY(k_out.ensure(m)); CVB_TRY(w_out.ensure(m * wbytes)); CVB_TRY(head.ensure(m)); CVB_TRY(seg.ensure(m));
   size_t tcap = tmp.cap;
-  CVB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tcap, flag.p, rank.p, static_cast<int>(nv), st));
-  k_vertex_newid<<<grid_for(nv, 256), 256, 0, st>>>(cvect, first.p, rank.p, nv, vnew.p);
-  e->launches += 2;
-  int32_t last_rank = 0, last_flag = 0;
-  CVB_CUDA(cudaMemcpyAsync(&last_rank, rank.p + (nv - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CVB_CUDA(cudaMemcpyAsync(&last_flag, flag.p + (nv - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (u32)
+    CVB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tcap, k_in, k_out.p, reinterpret_cast<const uint32_t *>(w_in),
+                                             reinterpret_cast<uint32_t *>(w_out.p), static_cast<int>(m), 0, bits, st));
+  else
+    CVB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tcap, k_in, k_out.p, reinterpret_cast<const double *>(w_in),
+                                             reinterpret_cast<double *>(w_out.p), static_cast<int>(m), 0, bits, st));
+  k_heads<<<grid_for(m, 256), 256, 0, st>>>(k_out.p, m, head.p);
+  tcap = tmp.cap;
+  CVB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tcap, head.p, seg.p, static_cast<int>(m), st));
+  e->launches += 3;
+  int32_t nseg32 = 0;
+  CVB_CUDA(cudaMemcpyAsync(&nseg32, seg.p + (m - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CVB_CUDA(cudaStreamSynchronize(st));
-  const int64_t nnv = static_cast<int64_t>(last_rank) + last_flag;
+  const int64_t mu = nseg32;
+  CVB_TRY(ukeys.ensure(mu + 1)); CVB_TRY(uw.ensure((mu + 1) * wbytes)); CVB_TRY(seg_start.ensure(mu + 1));
+  k_emit_pairs<<<grid_for(m, 256), 256, 0, st>>>(k_out.p, head.p, seg.p, m, ukeys.p, seg_start.p);
+  if (u32)
+    k_sum_segments_u32<<<static_cast<int>((mu * 32 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<uint32_t *>(w_out.p), seg_start.p, mu, m, reinterpret_cast<uint32_t *>(uw.p));
+  else
+    k_sum_segments_f64<<<grid_for(mu, 256), 256, 0, st>>>(reinterpret_cast<double *>(w_out.p), seg_start.p, mu, m,
+                                                         reinterpret_cast<double *>(uw.p));
+  e->launches += 2;
+  CVB_CUDA(cudaGetLastError());
+  *mu_out = mu;
+  return CVB_OK;
+}
+
+// Stage 2 — fill_newEdgesMap (rebuild.cpp:244-279) for the rows this engine holds: entry
+// (i -> t, w) becomes (vnew[base+i] -> vnew[t], w); parallel entries are merged.  The distinct
+// pairs (key = src << 32 | dst, ascending) land in e->pair_keys / e->pair_w.
+static int contract_impl(cvb_engine *e, const int32_t *vnew_global, int64_t nnv, int64_t *m_out) {
+  cudaStream_t st = e->stream;
+  const int64_t nv = e->nvl, ne = e->ne;
+  *m_out = 0;
+  e->pair_count = 0;
+  if (ne == 0) return CVB_OK;
+  DevBuf<uint64_t> k_in;
+  struct Guard { DevBuf<uint64_t> &b; ~Guard() { b.release(); } } guard{k_in};
+  CVB_TRY(k_in.ensure(ne));
+  k_edge_keys<<<static_cast<int>((nv * 32 + 255) / 256), 256, 0, st>>>(e->offsets.p, e->tails.p, vnew_global, e->base, nv,
+                                                                      k_in.p);
+  e->launches++;
+  int bits = 33;  // high word holds src < nnv
+  while ((int64_t(1) << (bits - 32)) < nnv && bits < 64) ++bits;
+  CVB_TRY(sort_reduce_pairs(e, k_in.p, e->weights.p, ne, bits, e->pair_keys, e->pair_w, m_out));
+  e->pair_count = *m_out;
+  return CVB_OK;
+}
+
+// Stage 3 — send_newEdges (rebuild.cpp:405-427): the pairs whose src lies in
+// [base, base + nv_local) become the engine's graph, adjacency sorted by tail.  `unique`
+// says the pairs are already distinct and ascending (one rank); otherwise (pairs received
+// from several ranks) they are sorted and merged first.
+static int install_pairs_impl(cvb_engine *e, int64_t nv_local, int64_t base, int64_t nv_global, const uint64_t *keys,
+                              const void *w, int64_t m, bool unique) {
+  cudaStream_t st = e->stream;
+  const size_t wbytes = e->mode == CVB_WEIGHTS_U32 ? 4 : 8;
+  CVB_TRY(check_sizes(nv_local, base, nv_global));
+  DevBuf<uint64_t> ukeys;
+  DevBuf<unsigned char> uw, tmp;
+  DevBuf<unsigned long long> row_count;
+  DevBuf<int64_t> noff;
+  auto release = [&]() { ukeys.release(); uw.release(); tmp.release(); row_count.release(); noff.release(); };
+  struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
+  int64_t mu = m;
+  if (!unique && m > 0) {
+    int bits = 33;
+    while ((int64_t(1) << (bits - 32)) < nv_global && bits < 64) ++bits;
+    CVB_TRY(sort_reduce_pairs(e, keys, w, m, bits, ukeys, uw, &mu));
+    keys = ukeys.p;
+    w = uw.p;
+  }
+  CVB_TRY(noff.ensure(nv_local + 2));
+  CVB_TRY(row_count.ensure(nv_local + 2));
+  CVB_CUDA(cudaMemsetAsync(row_count.p, 0, (nv_local + 2) * sizeof(unsigned long long), st));
+  CVB_TRY(e->tails.ensure(mu + 1));
+  CVB_TRY(e->d_flags.ensure(4));
+  CVB_CUDA(cudaMemsetAsync(e->d_flags.p + 2, 0, sizeof(int), st));
+  if (mu > 0) {
+    k_pairs_to_rows<<<grid_for(mu, 256), 256, 0, st>>>(keys, mu, base, nv_local, e->tails.p, row_count.p, e->d_flags.p + 2);
+    e->launches++;
+  }
+  size_t tb5 = 0;
+  CVB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb5, (unsigned long long *)nullptr, (int64_t *)nullptr,
+                                         static_cast<int>(nv_local + 1), st));
+  CVB_TRY(tmp.ensure(tb5 + 1024));
+  size_t tcap = tmp.cap;
+  CVB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tcap, row_count.p, noff.p, static_cast<int>(nv_local + 1), st));
+  e->launches++;
+  e->nvl = nv_local;
+  e->nvg = nv_global;
+  e->base = base;
+  e->ne = mu;
+  e->graph_ready = false;
+  CVB_TRY(e->offsets.ensure(nv_local + 2));
+  CVB_CUDA(cudaMemcpyAsync(e->offsets.p, noff.p, (nv_local + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  if (w != e->weights.p) {  // (one rank: pair_w is a different buffer from the old graph's weights)
+    CVB_TRY(e->weights.ensure((mu + 1) * wbytes));
+    if (mu > 0) CVB_CUDA(cudaMemcpyAsync(e->weights.p, w, mu * wbytes, cudaMemcpyDeviceToDevice, st));
+  }
+  int bad = 0;
+  CVB_CUDA(cudaMemcpyAsync(&bad, e->d_flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CVB_CUDA(cudaStreamSynchronize(st));
+  CVB_CHECK(bad == 0, CVB_ERR_ARG, "cvb_graph_from_pairs: a pair's source lies outside [base, base + nv_local)");
+  CVB_CUDA(cudaGetLastError());
+  return post_graph(e);
+}
+
+static int coarsen_impl(cvb_engine *e, int64_t *new_nv_out, int32_t *d_compose, int64_t n_compose) {
+  CVB_CHECK(e && e->phase_ready, CVB_ERR_STATE, "cvb_coarsen: run a phase first");
+  CVB_CHECK(e->nvl == e->nvg, CVB_ERR_STATE, "cvb_coarsen is the one-GPU path (N ranks: cvb_renumber + "
+            "cvb_contract_local + cvb_graph_from_pairs)");
+  cudaStream_t st = e->stream;
+  const int64_t nv = e->nvl;
+  DevBuf<int32_t> vnew;
+  struct Guard { DevBuf<int32_t> &b; ~Guard() { b.release(); } } guard{vnew};
+  CVB_TRY(vnew.ensure(nv + 1));
+  int64_t nnv = 0, m = 0;
+  CVB_TRY(renumber_impl(e, e->lab[e->past].p, nv, vnew.p, &nnv));  // cvect = pastComm, louvain.cpp:741
   if (d_compose) {
     k_compose<<<grid_for(n_compose, 256), 256, 0, st>>>(d_compose, vnew.p, n_compose);
     e->launches++;
   }
-  // fill_newEdgesMap: relabel every entry, sort by (src, dst), merge
-  int64_t nne = 0;
-  CVB_TRY(noff.ensure(nnv + 2));
-  CVB_TRY(row_count.ensure(nnv + 2));
-  CVB_CUDA(cudaMemsetAsync(row_count.p, 0, (nnv + 2) * sizeof(unsigned long long), st));
-  if (ne > 0) {
-    CVB_TRY(k_in.ensure(ne)); CVB_TRY(k_out.ensure(ne)); CVB_TRY(w_out.ensure(ne * wbytes));
-    CVB_TRY(head.ensure(ne)); CVB_TRY(seg.ensure(ne));
-    k_edge_keys<<<static_cast<int>((nv * 32 + 255) / 256), 256, 0, st>>>(e->offsets.p, e->tails.p, vnew.p, nv, k_in.p);
-    e->launches++;
-    int bits = 33;  // high word holds src < nnv
-    while ((int64_t(1) << (bits - 32)) < nnv && bits < 64) ++bits;
-    tcap = tmp.cap;
-    if (u32)
-      CVB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tcap, k_in.p, k_out.p, reinterpret_cast<uint32_t *>(e->weights.p),
-                                               reinterpret_cast<uint32_t *>(w_out.p), static_cast<int>(ne), 0, bits, st));
-    else
-      CVB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tcap, k_in.p, k_out.p, reinterpret_cast<double *>(e->weights.p),
-                                               reinterpret_cast<double *>(w_out.p), static_cast<int>(ne), 0, bits, st));
-    k_heads<<<grid_for(ne, 256), 256, 0, st>>>(k_out.p, ne, head.p);
-    tcap = tmp.cap;
-    CVB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tcap, head.p, seg.p, static_cast<int>(ne), st));
-    e->launches += 3;
-    int32_t nseg32 = 0;
-    CVB_CUDA(cudaMemcpyAsync(&nseg32, seg.p + (ne - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CVB_CUDA(cudaStreamSynchronize(st));
-    nne = nseg32;
-    CVB_TRY(ntails.ensure(nne + 1)); CVB_TRY(seg_start.ensure(nne + 1)); CVB_TRY(nw.ensure((nne + 1) * wbytes));
-    k_emit_entries<<<grid_for(ne, 256), 256, 0, st>>>(k_out.p, head.p, seg.p, ne, ntails.p, seg_start.p, row_count.p);
-    if (u32)
-      k_sum_segments_u32<<<static_cast<int>((nne * 32 + 255) / 256), 256, 0, st>>>(
-          reinterpret_cast<uint32_t *>(w_out.p), seg_start.p, nne, ne, reinterpret_cast<uint32_t *>(nw.p));
-    else
-      k_sum_segments_f64<<<grid_for(nne, 256), 256, 0, st>>>(reinterpret_cast<double *>(w_out.p), seg_start.p, nne, ne,
-                                                           reinterpret_cast<double *>(nw.p));
-    e->launches += 2;
-  }
-  // send_newEdges: CSR offsets from the per-row counts
-  size_t tb5 = 0;
-  CVB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb5, (unsigned long long *)nullptr, (int64_t *)nullptr,
-                                         static_cast<int>(nnv + 1), st));
-  CVB_TRY(tmp.ensure(tb5 + 1024));
-  tcap = tmp.cap;
-  CVB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tcap, row_count.p, noff.p, static_cast<int>(nnv + 1), st));
-  e->launches++;
-  // install as the engine's graph
-  e->nvl = e->nvg = nnv;
-  e->base = 0;
-  e->ne = nne;
-  e->graph_ready = false;
-  CVB_TRY(e->offsets.ensure(nnv + 2));
-  CVB_TRY(e->tails.ensure(nne + 1));
-  CVB_TRY(e->weights.ensure((nne + 1) * wbytes));
-  CVB_CUDA(cudaMemcpyAsync(e->offsets.p, noff.p, (nnv + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-  if (nne > 0) {
-    CVB_CUDA(cudaMemcpyAsync(e->tails.p, ntails.p, nne * sizeof(vid_t), cudaMemcpyDeviceToDevice, st));
-    CVB_CUDA(cudaMemcpyAsync(e->weights.p, nw.p, nne * wbytes, cudaMemcpyDeviceToDevice, st));
-  }
-  CVB_CUDA(cudaGetLastError());
-  CVB_TRY(post_graph(e));
+  CVB_TRY(contract_impl(e, vnew.p, nnv, &m));
+  CVB_TRY(install_pairs_impl(e, nnv, 0, nnv, e->pair_keys.p, e->pair_w.p, m, true));
   if (new_nv_out) *new_nv_out = nnv;
   return CVB_OK;
+}
+
+int cvb_renumber(cvb_engine *e, const int32_t *d_labels, int64_t n, int32_t *d_newid, int64_t *n_comm_out) {
+  CVB_CHECK(e && d_labels && d_newid && n_comm_out && n >= 0, CVB_ERR_ARG, "cvb_renumber: bad argument");
+  return renumber_impl(e, d_labels, n, d_newid, n_comm_out);
+}
+
+int cvb_contract_local(cvb_engine *e, const int32_t *d_newid_global, int64_t n_comm, int64_t *n_pairs_out) {
+  CVB_CHECK(e && e->graph_ready && d_newid_global && n_pairs_out, CVB_ERR_ARG, "cvb_contract_local: bad argument");
+  return contract_impl(e, d_newid_global, n_comm, n_pairs_out);
+}
+
+int cvb_graph_from_pairs(cvb_engine *e, int64_t nv_local, int64_t base, int64_t nv_global, const uint64_t *d_keys,
+                         const void *d_weights, int64_t n_pairs) {
+  CVB_CHECK(e && n_pairs >= 0 && (n_pairs == 0 || (d_keys && d_weights)), CVB_ERR_ARG, "cvb_graph_from_pairs: bad argument");
+  CVB_TRY(e->d_flags.ensure(4));
+  return install_pairs_impl(e, nv_local, base, nv_global, d_keys, d_weights, n_pairs, false);
 }
 
 int cvb_coarsen(cvb_engine *e, int64_t *new_nv_out) { return coarsen_impl(e, new_nv_out, nullptr, 0); }

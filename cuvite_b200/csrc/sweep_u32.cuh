@@ -864,7 +864,8 @@ struct GiantTables {
   const int32_t *__restrict__ chunk_owner;  // [total_chunks] giant index of every chunk
   const int64_t *__restrict__ chunk_start;  // [ngiant+1] prefix of chunks per vertex
   const int64_t *__restrict__ table_start;  // [ngiant+1] prefix of table slots per vertex
-  uint2 *__restrict__ slots;  // {key, weight}: 8-byte records keep the tables of all big vertices L2-resident
+  uint2 *__restrict__ slots;  // {key, weight} arena shared by the batches: slot s of the layout lives at slots[s - slot_base]
+  int64_t slot_base;          // first layout slot of the batch being processed
   uint32_t *__restrict__ gmeta;
   double *__restrict__ piece_gain;   // [total_slots / kGiantPiece]
   uint32_t *__restrict__ piece_key;  // [total_slots / kGiantPiece]
@@ -960,7 +961,8 @@ __device__ __forceinline__ void gtable_insert_chunk(uint2 *__restrict__ slots, c
 // vertex's global table — so the number of L2 atomics is the number of distinct
 // communities per chunk, and they are issued with 8 independent ones in flight.
 __global__ void __launch_bounds__(512, 2) k_sweep_u32_giant_insert(SweepU32Params p, const vid_t *__restrict__ list,
-                                                                  int n, GiantTables gt, int64_t total_chunks) {
+                                                                  int n, GiantTables gt, int64_t chunk_lo,
+                                                                  int64_t chunk_hi) {
   constexpr int TPV = 512, KC = 4, NCH = kGiantChunk / (TPV * KC), K = KC * NCH;
   constexpr int CAP = 2 * kGiantChunk;
   constexpr uint32_t capb = CAP * 4u;
@@ -976,7 +978,7 @@ __global__ void __launch_bounds__(512, 2) k_sweep_u32_giant_insert(SweepU32Param
   __syncthreads();
   constexpr int log2cap_s = 13;  // CAP = 8192
   constexpr uint32_t maskb = (CAP - 1u) << 2;
-  for (int64_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+  for (int64_t chunk = chunk_lo + blockIdx.x; chunk < chunk_hi; chunk += gridDim.x) {
     const int gi = gt.chunk_owner[chunk];
     const vid_t v = list[gi];
     const eid_t ve0 = p.offsets[v], ve1 = p.offsets[v + 1];
@@ -1048,7 +1050,7 @@ __global__ void __launch_bounds__(512, 2) k_sweep_u32_giant_insert(SweepU32Param
         sts_u32(a + capb, 0u);
       }
     }
-    gtable_insert_chunk<K>(gt.slots + tbase, ckey, tot, freshmask, glog2, gmask);
+    gtable_insert_chunk<K>(gt.slots + (tbase - gt.slot_base), ckey, tot, freshmask, glog2, gmask);
     __syncthreads();
   }
 }
@@ -1058,10 +1060,11 @@ __global__ void __launch_bounds__(512, 2) k_sweep_u32_giant_insert(SweepU32Param
 // per SM.  (A/B against k_sweep_u32_giant_insert: CVB_GIANT_DIRECT=1.)
 __global__ void __launch_bounds__(512, 4) k_sweep_u32_giant_insert_direct(SweepU32Params p,
                                                                          const vid_t *__restrict__ list, int n,
-                                                                         GiantTables gt, int64_t total_chunks) {
+                                                                         GiantTables gt, int64_t chunk_lo,
+                                                                         int64_t chunk_hi) {
   constexpr int K = kGiantChunk / 512;
   const unsigned lane = threadIdx.x & 31u;
-  for (int64_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+  for (int64_t chunk = chunk_lo + blockIdx.x; chunk < chunk_hi; chunk += gridDim.x) {
     const int gi = gt.chunk_owner[chunk];
     const vid_t v = list[gi];
     const eid_t ve0 = p.offsets[v], ve1 = p.offsets[v + 1];
@@ -1101,7 +1104,7 @@ __global__ void __launch_bounds__(512, 4) k_sweep_u32_giant_insert_direct(SweepU
       selfsum += (valid && tail[k] == self) ? w[k] : 0u;
       active |= (valid && !own) ? (1u << k) : 0u;
     }
-    gtable_insert_chunk<K>(gt.slots + tbase, key, w, active, glog2, gmask);
+    gtable_insert_chunk<K>(gt.slots + (tbase - gt.slot_base), key, w, active, glog2, gmask);
     const uint32_t c0u = __reduce_add_sync(0xffffffffu, ownsum);
     const uint32_t slu = __reduce_add_sync(0xffffffffu, selfsum);
     if (lane == 0) {
@@ -1112,14 +1115,15 @@ __global__ void __launch_bounds__(512, 4) k_sweep_u32_giant_insert_direct(SweepU
 }
 
 __global__ void __launch_bounds__(512) k_sweep_u32_giant_eval(SweepU32Params p, const vid_t *__restrict__ list, int n,
-                                                             GiantTables gt, int64_t total_pieces) {
+                                                             GiantTables gt, int64_t piece_lo, int64_t piece_hi) {
   __shared__ double red_g[16];
   __shared__ uint32_t red_id[16];
   const unsigned lane = threadIdx.x & 31u;
   const int wib = threadIdx.x >> 5;
-  for (int64_t piece = blockIdx.x; piece < total_pieces; piece += gridDim.x) {
+  for (int64_t piece = piece_lo + blockIdx.x; piece < piece_hi; piece += gridDim.x) {
     const int64_t s0 = piece * kGiantPiece;
     const int gi = giant_owner(gt.table_start, n, s0);
+    uint2 *__restrict__ tslots = gt.slots + (s0 - gt.slot_base);
     const vid_t v = list[gi];
     const uint2 me = p.packed[v + p.base];
     const double vd = p.vdeg[v];
@@ -1134,13 +1138,13 @@ __global__ void __launch_bounds__(512) k_sweep_u32_giant_eval(SweepU32Params p, 
       uint2 r[4];
       double ayv[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) r[j] = __ldcg(&gt.slots[s0 + threadIdx.x + (j0 + j) * 512]);
+      for (int j = 0; j < 4; ++j) r[j] = __ldcg(&tslots[threadIdx.x + (j0 + j) * 512]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         ayv[j] = 0.0;
         if (r[j].x != kEmptyKeyU) {
           ayv[j] = p.cdeg[r[j].x & kLabelMask];
-          gt.slots[s0 + threadIdx.x + (j0 + j) * 512] = make_uint2(kEmptyKeyU, 0u);
+          tslots[threadIdx.x + (j0 + j) * 512] = make_uint2(kEmptyKeyU, 0u);
         }
       }
 #pragma unroll

@@ -48,16 +48,22 @@ def tensor_of(engine, name: str) -> torch.Tensor:
 
 
 class DistLouvain:
-    """One phase of distributed Louvain over ``world`` vertex-range partitions."""
+    """Distributed Louvain over ``world`` vertex-range partitions: phases (``run_phase``),
+    the coarsening between them (``coarsen``) and the level loop (``run``)."""
 
     def __init__(self, engine, rank: int, world: int, nv_global: int, group=None, exchange: str = "labels"):
-        self.e, self.rank, self.world, self.nvg, self.group = engine, rank, world, nv_global, group
+        self.e, self.rank, self.world, self.group = engine, rank, world, group
         assert exchange in ("labels", "deltas")
         self.labels_only = exchange == "labels"
-        self.parts = partition_ranges(nv_global, world)
-        self.base, self.bound = self.parts[rank], self.parts[rank + 1]
-        self.even = len({self.parts[p + 1] - self.parts[p] for p in range(world)}) == 1
         self.constant = None
+        self.timing = [] if os.environ.get("CVB_DIST_TIMING") == "1" else None
+        self._set_nv_global(nv_global)
+
+    def _set_nv_global(self, nv_global: int):
+        self.nvg = nv_global
+        self.parts = partition_ranges(nv_global, self.world)
+        self.base, self.bound = self.parts[self.rank], self.parts[self.rank + 1]
+        self.even = len({self.parts[p + 1] - self.parts[p] for p in range(self.world)}) == 1
 
     # -- collectives -------------------------------------------------------------
     def _all_gather_rows(self, global_t: torch.Tensor, local_t: torch.Tensor):
@@ -93,17 +99,39 @@ class DistLouvain:
             if self.labels_only:
                 tensor_of(e, "vdeg_global").copy_(tensor_of(e, "cdeg"))
 
+    def _mark(self, name):
+        """CVB_DIST_TIMING=1: CUDA-event stamps between the stages of a sweep (bench diagnostics)."""
+        if self.timing is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.timing.append((name, ev))
+
+    def stage_times_ms(self):
+        """Mean milliseconds per stage over the sweeps stamped so far (after a synchronize)."""
+        out, prev = {}, None
+        for name, ev in self.timing or []:
+            if name != "begin" and prev is not None:
+                out.setdefault(name, []).append(prev.elapsed_time(ev))
+            prev = ev
+        return {k: sum(v) / len(v) for k, v in out.items()}
+
     def sweep(self):
         """One synchronous sweep + exchange.  Returns the modularity of this iteration."""
         e = self.e
+        self._mark("begin")
         e.sweep()
+        self._mark("sweep_kernels")
         if self.world > 1 and self.labels_only:
             self._all_gather_rows(tensor_of(e, "labels_global_next"), tensor_of(e, "labels_target"))
+            self._mark("all_gather_labels")
             if hasattr(e, "rebuild_and_reduce_async"):  # sums stay on the device: one read-back per sweep
                 e.rebuild_and_reduce_async()
+                self._mark("label_diff_and_reduce")
                 s = tensor_of(e, "sums")
                 self._all_reduce(s)
+                self._mark("all_reduce_sums")
                 sums = s.cpu().numpy()
+                self._mark("read_back")
                 c = self.constant
                 return (sums[0] * c) - (sums[1] * c * c)
             sums = e.rebuild_and_reduce()
@@ -140,6 +168,72 @@ class DistLouvain:
                 break
             self.advance()
         return prev, iters
+
+
+    # -- coarsening between phases -------------------------------------------------
+    def coarsen(self):
+        """distbuildNextLevelGraph across ranks (rebuild.cpp:27-454), with the ONE-rank
+        community numbering so that an N-rank run reproduces the 1-rank reference:
+
+        1. all-gather cvect (= the local PAST labels) and renumber the communities in order of
+           first appearance — every rank computes the same numbering from the same array;
+        2. contract the local rows to distinct (new src, new dst, weight) pairs on the device;
+        3. one all-to-all moves every pair to the owner of its new source under the
+           reference's partition of the new graph, ``parts[p] = nc*p // P`` (rebuild.cpp:294-295);
+        4. the owner merges what it received and emits its CSR rows (sorted by tail).
+
+        Returns (newid, nc): newid[i] = new vertex of old GLOBAL vertex i (replicated tensor)."""
+        e = self.e
+        cv_local = tensor_of(e, "labels_past")
+        cv_global = torch.empty(self.nvg, dtype=cv_local.dtype, device=cv_local.device)
+        self._all_gather_rows(cv_global, cv_local)
+        newid, nc = e.renumber(cv_global)
+        keys, w = e.contract_local(newid, nc)
+        parts = partition_ranges(nc, self.world)
+        if self.world > 1:
+            cuts = torch.tensor(parts[1:-1], dtype=torch.int64, device=keys.device) << 32
+            idx = torch.searchsorted(keys, cuts).tolist()  # keys ascend, source in the high word
+            edges = [0] + idx + [keys.numel()]
+            send = [edges[p + 1] - edges[p] for p in range(self.world)]
+            recv_t = torch.empty(self.world, dtype=torch.int64, device=keys.device)
+            dist.all_to_all_single(recv_t, torch.tensor(send, dtype=torch.int64, device=keys.device), group=self.group)
+            recv = recv_t.tolist()
+            rkeys = torch.empty(sum(recv), dtype=keys.dtype, device=keys.device)
+            rw = torch.empty(sum(recv), dtype=w.dtype, device=w.device)
+            dist.all_to_all_single(rkeys, keys.contiguous(), recv, send, group=self.group)
+            dist.all_to_all_single(rw, w.contiguous(), recv, send, group=self.group)
+            keys, w = rkeys, rw
+        e.graph_from_pairs(parts[self.rank + 1] - parts[self.rank], parts[self.rank], nc, keys, w)
+        self._set_nv_global(nc)
+        return newid, nc
+
+    def run(self, max_levels: int = 200, threshold: float = 1.0e-6):
+        """The default phase loop of main.cpp:218-495 across ranks.  Returns (level_q,
+        level_iters (cumulative, as the reference prints them), level_nv, comm) where
+        comm[i] is the final community of original GLOBAL vertex i (replicated tensor)."""
+        level_q, level_iters, level_nv = [], [], []
+        comm, nv0 = None, self.nvg
+        curr, prev, tot_iters, phase = -1.0, -1.0, 0, 0
+        while True:
+            nv = self.nvg
+            curr, iters = self.run_phase(lower=curr, thresh=threshold)
+            tot_iters += iters
+            if (curr - prev) > threshold:  # main.cpp:361
+                newid, _ = self.coarsen()  # main.cpp:413
+                comm = newid.clone() if comm is None else newid[comm.long()]  # main.cpp:401-404
+            else:
+                break
+            if phase < max_levels:
+                level_q.append(curr)
+                level_iters.append(tot_iters)
+                level_nv.append(nv)
+            prev, curr = curr, -1.0
+            phase += 1
+            if phase == 200 or tot_iters > 10000:  # main.cpp:486
+                break
+        if comm is None:  # no level improved: every vertex is its own community
+            comm = torch.arange(nv0, dtype=torch.int64)
+        return level_q, level_iters, level_nv, comm
 
 
 def init_process_group(backend: str | None = None):
@@ -213,6 +307,8 @@ def bench_multi(args, metric, unit, base_scale, measured_peak_gbs, ClockSampler)
     dl.phase_begin()
     st = {"prev": -1.0, "sweep_ms": [], "phases": 0}
     launches0 = gpu.launch_count
+    if dl.timing is not None:
+        dl.timing = []
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -251,7 +347,8 @@ def bench_multi(args, metric, unit, base_scale, measured_peak_gbs, ClockSampler)
                                           "allreduce(deltas)+allgather(labels)",
                            "l2": "per-GPU inputs larger than L2; no flush",
                            "sweep_kernels_ms_max_rank": sweep_ms, "max_local_entries": int(ne_max.item()),
-                           "phase_restarts_in_timed_region": st["phases"]},
+                           "phase_restarts_in_timed_region": st["phases"],
+                           **({"stage_ms_rank0": dl.stage_times_ms()} if dl.timing is not None else {})},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                              "kernel": "sweep kernel group of the slowest rank, 12E+40V local bytes"},

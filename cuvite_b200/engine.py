@@ -26,7 +26,8 @@ from ._lib import GraphInfo, check
 WEIGHTS_U32, WEIGHTS_F64 = 1, 2
 LABELS_PAST, LABELS_CURR, LABELS_TARGET = 0, 1, 2
 BUF = dict(labels_global=0, labels_curr=1, labels_target=2, labels_past=3, cdeg=4, csize=5, ddeg=6, dsize=7,
-           vdeg=8, cw=9, offsets=10, tails=11, weights=12, labels_global_next=13, vdeg_global=14, sums=15)
+           vdeg=8, cw=9, offsets=10, tails=11, weights=12, labels_global_next=13, vdeg_global=14, sums=15,
+           pair_keys=16, pair_weights=17)
 CLASS_NAMES = ["deg0", "d4", "d8", "d16", "d32", "d64", "d128", "d256", "d512", "d1k", "d2k", "d4k", "d8k", "c16k", "c32k", "c64k", "giant"]
 
 
@@ -168,6 +169,45 @@ class GpuGraph:
         if n < 0:
             check(n, "louvain_run")
         return list(lq[:n]), [int(x) for x in li[:n]], [int(x) for x in ln[:n]], comm
+
+    # ---- N-rank coarsening stages (device tensors in, device tensors out) ------
+    def renumber(self, labels):
+        """cvb_renumber: ``labels`` is a CUDA int32 tensor (the all-gathered cvect).  Returns
+        (newid int32 tensor, number of communities)."""
+        import torch
+        assert labels.is_cuda and labels.dtype == torch.int32 and labels.is_contiguous()
+        newid = torch.empty_like(labels)
+        torch.cuda.current_stream().synchronize()  # the engine stream may differ from torch's
+        n = C.c_int64(0)
+        check(self._L.cvb_renumber(self._h, labels.data_ptr(), labels.numel(), newid.data_ptr(), C.byref(n)), "renumber")
+        return newid, n.value
+
+    def contract_local(self, newid, n_comm: int):
+        """cvb_contract_local: distinct (src << 32 | dst) pairs of this engine's rows under
+        ``newid``.  Returns (keys int64 tensor, weights tensor) — zero-copy views of engine
+        buffers, valid until the next coarsening call."""
+        import torch
+        m = C.c_int64(0)
+        torch.cuda.current_stream().synchronize()
+        check(self._L.cvb_contract_local(self._h, newid.data_ptr(), n_comm, C.byref(m)), "contract_local")
+        wt = "<u4" if self.info().weight_mode == WEIGHTS_U32 else "<f8"
+        if m.value == 0:
+            return (torch.empty(0, dtype=torch.int64, device="cuda"),
+                    torch.empty(0, dtype=torch.int32 if wt == "<u4" else torch.float64, device="cuda"))
+        keys = torch.as_tensor(DeviceArray(int(self._L.cvb_buffer(self._h, BUF["pair_keys"])), (m.value,), "<i8"),
+                               device="cuda")
+        w = torch.as_tensor(DeviceArray(int(self._L.cvb_buffer(self._h, BUF["pair_weights"])), (m.value,),
+                                        "<i4" if wt == "<u4" else "<f8"), device="cuda")
+        return keys, w
+
+    def graph_from_pairs(self, nv_local: int, base: int, nv_global: int, keys, weights):
+        """cvb_graph_from_pairs: the pairs routed to this rank become the engine's graph."""
+        import torch
+        torch.cuda.current_stream().synchronize()
+        keys, weights = keys.contiguous(), weights.contiguous()
+        check(self._L.cvb_graph_from_pairs(self._h, nv_local, base, nv_global, keys.data_ptr() if keys.numel() else None,
+                                           weights.data_ptr() if keys.numel() else None, keys.numel()),
+              "graph_from_pairs")
 
     def download_graph(self):
         gi = self.info()

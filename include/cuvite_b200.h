@@ -173,7 +173,9 @@ enum {
   CVB_BUF_WEIGHTS = 12,      /* uint32 or double [ne_local], see weight_mode        */
   CVB_BUF_LABELS_GLOBAL_NEXT = 13, /* int32[nv_global] gather target for the NEXT labels (N>1) */
   CVB_BUF_VDEG_GLOBAL = 14,  /* double[nv_global] every vertex's degree (N>1, replicated)   */
-  CVB_BUF_SUMS = 15          /* double[2] device copy of the last {sum clusterWeight, sum degree^2} */
+  CVB_BUF_SUMS = 15,         /* double[2] device copy of the last {sum clusterWeight, sum degree^2} */
+  CVB_BUF_PAIR_KEYS = 16,    /* uint64[n_pairs] (src << 32 | dst) of cvb_contract_local, ascending */
+  CVB_BUF_PAIR_WEIGHTS = 17  /* uint32 or double [n_pairs], see weight_mode                        */
 };
 void *cvb_buffer(cvb_engine *e, int which);
 void *cvb_stream(cvb_engine *e);
@@ -222,6 +224,26 @@ int cvb_reduce_mod(cvb_engine *e, int64_t nv, const double *local_cdeg,
  * tail (rebuild.cpp:413-426) and make it the engine's graph.  new_nv_out gets
  * the number of communities. */
 int cvb_coarsen(cvb_engine *e, int64_t *new_nv_out);
+
+/* distbuildNextLevelGraph across N ranks (rebuild.cpp:27-454) in three device stages; the
+ * caller (cuvite_b200/dist.py) moves the contracted pairs between ranks with an NCCL
+ * all-to-all in place of the reference's MPI exchange (rebuild.cpp:281-403).
+ *
+ * 1. cvb_renumber       — distReNumber, rebuild.cpp:72-85 with the ONE-rank numbering (SURVEY
+ *    section 8c: the N-rank runs are compared with the 1-rank reference): d_newid[i] = rank,
+ *    in order of first appearance scanning i ascending, of d_labels[i].  d_labels is the
+ *    all-gathered cvect (DEVICE, int32[n], values in [0,n)); *n_comm_out = communities.
+ * 2. cvb_contract_local — fill_newEdgesMap, rebuild.cpp:244-279: every entry (i -> t, w) of
+ *    this engine's rows becomes (newid[base+i] -> newid[t], w), parallel entries merged;
+ *    the distinct pairs are left ascending in CVB_BUF_PAIR_KEYS / CVB_BUF_PAIR_WEIGHTS.
+ * 3. cvb_graph_from_pairs — send_newEdges, rebuild.cpp:405-427: the (DEVICE) pairs routed to
+ *    this rank — sources in [base, base + nv_local), any order, duplicates allowed — are
+ *    merged, emitted as a CSR sorted by tail and become the engine's graph.  Weights are in
+ *    the engine's weight mode (uint32 or double). */
+int cvb_renumber(cvb_engine *e, const int32_t *d_labels, int64_t n, int32_t *d_newid, int64_t *n_comm_out);
+int cvb_contract_local(cvb_engine *e, const int32_t *d_newid_global, int64_t n_comm, int64_t *n_pairs_out);
+int cvb_graph_from_pairs(cvb_engine *e, int64_t nv_local, int64_t base, int64_t nv_global,
+                         const uint64_t *d_keys, const void *d_weights, int64_t n_pairs);
 
 /* D2H of the engine's current graph in the boundary layout (for writing Vite
  * files / handing the next level back to the reference's DistGraph). */

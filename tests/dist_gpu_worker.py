@@ -1,5 +1,6 @@
 """torchrun worker: N-GPU phase 0 through cuvite_b200.dist must equal the 1-rank
-reference (golden fixture) bit for bit, and a scale-18 R-MAT phase must equal the oracle."""
+reference (golden fixture) bit for bit; the multi-level run (phases + distributed coarsening)
+must reproduce the reference's levels and final assignment."""
 import os
 import sys
 
@@ -32,6 +33,21 @@ def main():
             q, iters = DistLouvain(gpu, rank, world, nv, exchange=exchange).run_phase()
             good = iters == int(g["iters"]) and q == float(g["q"]) and np.array_equal(gpu.labels(0), g["cvect"][b0:b1])
             print(f"rank {rank} {name} [{exchange}]: q={q!r} iters={iters} ok={good}", flush=True)
+            ok &= bool(good)
+            gpu.close()
+        # phases + distributed coarsening: levels and final assignment of the 1-rank reference
+        for name in ("rmat10_intw", "hub30k", "er1k", "ring6x5"):
+            g = np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz"))
+            o, t, w = g["offsets"], g["tails"].astype(np.int64), g["weights"]
+            nv = o.size - 1
+            parts = partition_ranges(nv, world)
+            b0, b1 = parts[rank], parts[rank + 1]
+            gpu = GpuGraph(stream=stream.cuda_stream)
+            gpu.upload(o[b0:b1 + 1] - o[b0], t[o[b0]:o[b1]], w[o[b0]:o[b1]], base=b0, nv_global=nv)
+            lq, li, ln, comm = DistLouvain(gpu, rank, world, nv).run()
+            good = (lq == list(g["level_q"]) and li == list(g["level_iters"]) and ln == list(g["level_nv"])
+                    and np.array_equal(comm.cpu().numpy(), g["comm"]))
+            print(f"rank {rank} {name} [multi-level run]: q={lq} iters={li} nv={ln} ok={good}", flush=True)
             ok &= bool(good)
             gpu.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")

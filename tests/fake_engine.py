@@ -84,3 +84,32 @@ class OracleEngine:
 
     def last_sweep_ms(self):
         return 0.0
+
+    # ---- N-rank coarsening stages (numpy stand-ins for cvb_renumber / cvb_contract_local /
+    # ---- cvb_graph_from_pairs) -----------------------------------------------------------
+    def renumber(self, labels):
+        lab = labels.numpy()
+        uniq, first = np.unique(lab, return_index=True)
+        rank = np.empty(uniq.size, np.int64)
+        rank[np.argsort(first, kind="stable")] = np.arange(uniq.size)
+        return torch.from_numpy(rank[np.searchsorted(uniq, lab)]), int(uniq.size)
+
+    @staticmethod
+    def _merge(keys, w):
+        uk, inv = np.unique(keys, return_inverse=True)
+        return uk, np.bincount(inv, weights=w, minlength=uk.size)
+
+    def contract_local(self, newid, n_comm):
+        nid = newid.numpy()
+        src = np.repeat(nid[self.base:self.base + self.nvl], np.diff(self.off))
+        keys = (src.astype(np.int64) << 32) | nid[self.tl]
+        uk, uw = self._merge(keys, self.w)
+        return torch.from_numpy(uk), torch.from_numpy(uw)
+
+    def graph_from_pairs(self, nv_local, base, nv_global, keys, weights):
+        uk, uw = self._merge(keys.numpy(), weights.numpy())
+        src, dst = (uk >> 32) - base, uk & 0xFFFFFFFF
+        assert uk.size == 0 or (src.min() >= 0 and src.max() < nv_local)
+        off = np.zeros(nv_local + 1, np.int64)
+        np.cumsum(np.bincount(src, minlength=nv_local), out=off[1:])
+        self.upload(off, dst, uw, base=base, nv_global=nv_global)

@@ -52,6 +52,46 @@ def test_distributed_phase_equals_one_rank_reference(oracle, world, name, exchan
         assert ret[r][0], f"rank {r}: {ret[r]}"
 
 
+def _run_worker(rank, world, port, name, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cuvite_b200.dist import DistLouvain
+    from cuvite_b200.vite_io import partition_ranges
+    from fake_engine import OracleEngine
+    from oracle.binding import Oracle
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz"))
+    o, t, w = g["offsets"], g["tails"].astype(np.int64), g["weights"]
+    nv = o.size - 1
+    parts = partition_ranges(nv, world)
+    b0, b1 = parts[rank], parts[rank + 1]
+    orc = Oracle()
+    orc.set_num_threads(1)
+    eng = OracleEngine(orc).upload(o[b0:b1 + 1] - o[b0], t[o[b0]:o[b1]], w[o[b0]:o[b1]], base=b0, nv_global=nv)
+    lq, li, ln, comm = DistLouvain(eng, rank, world, nv).run()
+    ok = (lq == list(g["level_q"]) and li == list(g["level_iters"]) and ln == list(g["level_nv"])
+          and np.array_equal(comm.numpy(), g["comm"]))
+    ret[rank] = (bool(ok), lq, li, ln)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,name", [(2, "rmat10_intw"), (3, "er1k"), (2, "ring6x5"), (3, "hub30k")])
+def test_distributed_multilevel_run_equals_one_rank_reference(oracle, world, name):
+    """Phases + distributed coarsening (all-gathered cvect, 1-rank numbering, all-to-all of the
+    contracted pairs, owner-side merge) reproduce the one-rank reference's levels and final
+    assignment on any rank count."""
+    port = 29800 + world * 11 + len(name)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_run_worker, args=(world, port, name, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert ret[r][0], f"rank {r}: {ret[r]}"
+
+
 def test_partition_ranges_match_reference_formula():
     from cuvite_b200.vite_io import partition_ranges
     for nv, p in [(1024, 3), (7, 8), (1 << 20, 8), (30000, 7)]:

@@ -297,14 +297,17 @@ def test_tma_staged_variant_matches_reference(monkeypatch):
     gpu.close()
 
 
-@pytest.mark.parametrize("cluster", [False, True])
-def test_true_giant_hub_matches_oracle(oracle, cluster, monkeypatch):
-    """Vertices above 8192 entries: global-table path (default) and the thread-block-cluster /
+@pytest.mark.parametrize("cluster,arena_mb", [(False, 0), (True, 0), (False, 1)])
+def test_true_giant_hub_matches_oracle(oracle, cluster, arena_mb, monkeypatch):
+    """Vertices above 8192 entries: global-table path (default; arena_mb=1 forces one batch per
+    big vertex through the shared table arena) and the thread-block-cluster /
     distributed-shared-memory path (CVB_CLUSTER=1), incl. one vertex above 65536 entries."""
     import torch
     from cuvite_b200 import graphgen as gg
     from cuvite_b200.engine import GpuGraph
     monkeypatch.setenv("CVB_CLUSTER", "1" if cluster else "0")
+    if arena_mb:
+        monkeypatch.setenv("CVB_GIANT_ARENA_MB", str(arena_mb))
     gpu = GpuGraph()
     nv = 90000
     bg = gg.erdos_renyi(nv, 6.0, seed=11)
@@ -331,4 +334,21 @@ def test_true_giant_hub_matches_oracle(oracle, cluster, monkeypatch):
         gpu.rotate_labels()
     q, iters = gpu.phase_run()
     assert (q, iters) == (want.q, want.iters) and np.array_equal(gpu.labels(0), want.cvect)
+    gpu.close()
+
+
+@pytest.mark.parametrize("name", ["rmat10_intw", "hub30k", "er1k", "ring6x5", "empty_rows"])
+def test_staged_coarsening_driver_matches_golden(name):
+    """DistLouvain.run on one rank drives cvb_renumber / cvb_contract_local /
+    cvb_graph_from_pairs (the N-rank coarsening stages, here with the merge of stage 3
+    exercised on already-distinct pairs) and must reproduce the reference's levels."""
+    from cuvite_b200.dist import DistLouvain
+    from cuvite_b200.engine import GpuGraph
+    g = load_golden(name)
+    gpu = GpuGraph()
+    gpu.upload(*_csr(g))
+    nv = g["offsets"].size - 1
+    lq, li, ln, comm = DistLouvain(gpu, 0, 1, nv).run()
+    assert lq == list(g["level_q"]) and li == list(g["level_iters"]) and ln == list(g["level_nv"])
+    assert np.array_equal(comm.cpu().numpy(), g["comm"])
     gpu.close()
