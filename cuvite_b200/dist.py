@@ -57,6 +57,7 @@ class DistLouvain:
         self.labels_only = exchange == "labels"
         self.constant = None
         self.timing = [] if os.environ.get("CVB_DIST_TIMING") == "1" else None
+        self._pinned = None
         self._set_nv_global(nv_global)
 
     def _set_nv_global(self, nv_global: int):
@@ -130,7 +131,11 @@ class DistLouvain:
                 s = tensor_of(e, "sums")
                 self._all_reduce(s)
                 self._mark("all_reduce_sums")
-                sums = s.cpu().numpy()
+                if self._pinned is None:
+                    self._pinned = torch.empty(2, dtype=torch.float64).pin_memory()
+                self._pinned.copy_(s, non_blocking=True)  # pinned + stream sync: no pageable staging copy
+                torch.cuda.current_stream().synchronize()
+                sums = self._pinned.numpy()
                 self._mark("read_back")
                 c = self.constant
                 return (sums[0] * c) - (sums[1] * c * c)

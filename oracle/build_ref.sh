@@ -56,6 +56,21 @@ if [ -f "$REPO/cuvite_b200/libcuvite_b200.so" ]; then
        -L"$REPO/cuvite_b200" -lcuvite_b200 -Wl,-rpath,'$ORIGIN/../../cuvite_b200' \
        -Wl,-rpath,/usr/local/cuda/lib64 -o "$OUT/gc_gpu_dropin"
   echo "built $OUT/gc_gpu_dropin"
+  # outer-boundary drop-in: the GPU overload of distLouvainMethod comes from adapter_resident.cpp
+  # (resident engine, one upload per phase), so louvain.cpp is compiled WITHOUT -DRUNONGPU and
+  # main.cpp WITH it
+  OBJ="$TMP/obj_resident"; mkdir -p "$OBJ"
+  for f in coloring compare distgraph louvain rebuild utils; do
+    $CXX $FLAGS -c "$TMP/$f.cpp" -o "$OBJ/$f.o"
+  done
+  $CXX $FLAGS -DRUNONGPU=1 -I"$REPO/include" -c "$TMP/main.cpp" -o "$OBJ/main.o"
+  $CXX $FLAGS -DRUNONGPU=1 -I"$REPO/include" -c "$REPO/cuvite_b200/csrc/adapter.cpp" -o "$OBJ/adapter.o"
+  $CXX $FLAGS -DRUNONGPU=1 -I"$REPO/include" -c "$REPO/cuvite_b200/csrc/adapter_resident.cpp" -o "$OBJ/adapter_resident.o"
+  # adapter.o also defines gpu_for_louvain_iteration / gpu_reduce_mod: unused here, harmless
+  $CXX -fopenmp "$OBJ"/{main,coloring,compare,distgraph,louvain,rebuild,utils,adapter,adapter_resident}.o \
+       -L"$REPO/cuvite_b200" -lcuvite_b200 -Wl,-rpath,'$ORIGIN/../../cuvite_b200' \
+       -Wl,-rpath,/usr/local/cuda/lib64 -o "$OUT/gc_gpu_resident"
+  echo "built $OUT/gc_gpu_resident"
 fi
 # the reference's own CUDA path, recompiled for Blackwell (baseline only; SURVEY.md §8c "also compilable")
 if command -v nvcc >/dev/null 2>&1; then

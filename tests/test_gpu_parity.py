@@ -253,7 +253,9 @@ def test_reference_main_runs_on_our_plugin(tmp_path):
     """The reference's UNMODIFIED main.cpp/louvain.cpp/rebuild.cpp, built with -DRUNONGPU=1
     against include/GpuGraph.cuh + adapter.cpp + libcuvite_b200.so (oracle/_ref/gc_gpu_dropin),
     must print the same per-level lines and write the same .communities file as the
-    reference's CPU build (oracle/_ref/gc_cpu64) on the same Vite file."""
+    reference's CPU build (oracle/_ref/gc_cpu64) on the same Vite file — through the
+    per-iteration plugin (gc_gpu_dropin) and through the resident outer boundary
+    (gc_gpu_resident: adapter_resident.cpp supplies distLouvainMethod(.., GpuGraph&))."""
     import os
     import re
     import shutil
@@ -261,11 +263,12 @@ def test_reference_main_runs_on_our_plugin(tmp_path):
     from cuvite_b200 import graphgen as gg, vite_io
     ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
     cpu, dropin = os.path.join(ref, "gc_cpu64"), os.path.join(ref, "gc_gpu_dropin")
-    if not (os.path.exists(cpu) and os.path.exists(dropin)):
+    resident = os.path.join(ref, "gc_gpu_resident")  # outer boundary: distLouvainMethod(.., GpuGraph&) is ours
+    if not (os.path.exists(cpu) and os.path.exists(dropin) and os.path.exists(resident)):
         pytest.skip("oracle/_ref binaries not built (needs /root/reference at build time)")
     g = gg.rmat(14, seed=2)
     outs = {}
-    for tag, exe in (("cpu", cpu), ("gpu", dropin)):
+    for tag, exe in (("cpu", cpu), ("gpu", dropin), ("resident", resident)):
         d = tmp_path / tag
         d.mkdir()
         f = str(d / "g.bin")
@@ -276,8 +279,8 @@ def test_reference_main_runs_on_our_plugin(tmp_path):
         levels = re.findall(r"Level (\d+), Modularity: ([0-9.eE+-]+), Clustering time: [^,]*, Iterations: (\d+)", r.stdout)
         assert levels, r.stdout[-2000:]
         outs[tag] = (levels, open(f + ".communities").read())
-    assert outs["cpu"][0] == outs["gpu"][0]
-    assert outs["cpu"][1] == outs["gpu"][1]
+    assert outs["cpu"][0] == outs["gpu"][0] == outs["resident"][0]
+    assert outs["cpu"][1] == outs["gpu"][1] == outs["resident"][1]
 
 
 def test_tma_staged_variant_matches_reference(monkeypatch):

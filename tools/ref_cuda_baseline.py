@@ -3,7 +3,9 @@
 oracle/_ref/gc_gpu64 by oracle/build_ref.sh) run on this box's GPU on the same Vite file as
 
   * oracle/_ref/gc_gpu_dropin — the same reference main.cpp/louvain.cpp linked against
-    libcuvite_b200.so through the per-iteration plugin boundary, and
+    libcuvite_b200.so through the per-iteration plugin boundary,
+  * oracle/_ref/gc_gpu_resident — the same, with the GPU overload of distLouvainMethod supplied
+    by adapter_resident.cpp (one upload per phase), oracle/_ref/gc_cpu64 (the CPU reference), and
   * the resident engine (cvb_louvain_run).
 
 Test/measurement infrastructure: prints one JSON object; nothing here is on the product path.
@@ -60,7 +62,7 @@ def main():
     with tempfile.TemporaryDirectory() as d:
         f = os.path.join(d, "g.bin")
         vite_io.write_vite(f, g)
-        for tag in ("gc_gpu64", "gc_gpu_dropin"):
+        for tag in ("gc_gpu64", "gc_gpu_dropin", "gc_gpu_resident", "gc_cpu64"):
             exe = os.path.join(ref, tag)
             out[tag] = run_cli(exe, f, a.threads) if os.path.exists(exe) else {"unavailable": True}
     ks = out["gc_gpu64"].get("kernel_s_per_iteration")
