@@ -5,7 +5,7 @@
 // implemented on the resident engine: the graph of the phase is uploaded ONCE, all sweeps of
 // the phase run on the device (cvb_phase_run) and only cvect comes back — instead of the
 // reference's per-iteration gpu_for_louvain_iteration call with ~56 bytes/vertex over PCIe
-// per sweep.  Build (oracle/build_ref.sh -> oracle/_ref/gc_gpu_resident):
+// per sweep.  Build:
 //   main.cpp ... -DRUNONGPU=1 -I<repo>/include   (uses the GPU overload, constructs GpuGraph)
 //   louvain.cpp  WITHOUT -DRUNONGPU              (so that it does not define the overload)
 //   + adapter.cpp (set_gpuDevices) + this file + -lcuvite_b200

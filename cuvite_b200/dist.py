@@ -51,18 +51,23 @@ class DistLouvain:
     """Distributed Louvain over ``world`` vertex-range partitions: phases (``run_phase``),
     the coarsening between them (``coarsen``) and the level loop (``run``)."""
 
-    def __init__(self, engine, rank: int, world: int, nv_global: int, group=None, exchange: str = "labels"):
+    def __init__(self, engine, rank: int, world: int, nv_global: int, group=None, exchange: str = "labels",
+                 parts=None):
+        """``parts``: explicit vertex ranges of the CURRENT graph (e.g. the reference's -b
+        edge-balanced ranges, vite_io.balanced_ranges); default parts[p] = nv*p // P.  Coarsened
+        levels always use the default, like rebuild.cpp:294-295."""
         self.e, self.rank, self.world, self.group = engine, rank, world, group
         assert exchange in ("labels", "deltas")
         self.labels_only = exchange == "labels"
         self.constant = None
         self.timing = [] if os.environ.get("CVB_DIST_TIMING") == "1" else None
         self._pinned = None
-        self._set_nv_global(nv_global)
+        self._set_nv_global(nv_global, parts)
 
-    def _set_nv_global(self, nv_global: int):
+    def _set_nv_global(self, nv_global: int, parts=None):
         self.nvg = nv_global
-        self.parts = partition_ranges(nv_global, self.world)
+        self.parts = list(parts) if parts is not None else partition_ranges(nv_global, self.world)
+        assert len(self.parts) == self.world + 1 and self.parts[0] == 0 and self.parts[-1] == nv_global
         self.base, self.bound = self.parts[self.rank], self.parts[self.rank + 1]
         self.even = len({self.parts[p + 1] - self.parts[p] for p in range(self.world)}) == 1
 
@@ -258,9 +263,9 @@ def init_process_group(backend: str | None = None):
     return rank, local, world
 
 
-def load_partition(engine, g, rank: int, world: int):
+def load_partition(engine, g, rank: int, world: int, parts=None):
     """Upload rows [parts[rank], parts[rank+1]) of an in-memory (device) CSRGraph."""
-    parts = partition_ranges(g.nv, world)
+    parts = partition_ranges(g.nv, world) if parts is None else parts
     b0, b1 = parts[rank], parts[rank + 1]
     e0, e1 = int(g.offsets[b0]), int(g.offsets[b1])
     offs = (g.offsets[b0:b1 + 1] - e0).contiguous()

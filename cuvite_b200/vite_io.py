@@ -33,11 +33,42 @@ def partition_ranges(nv: int, nparts: int) -> list[int]:
     return [(nv * p) // nparts for p in range(nparts + 1)]
 
 
-def read_vite(path: str, rank: int = 0, nparts: int = 1) -> tuple[CSRGraph, int, int]:
-    """Returns (local rows as a CSRGraph with global tails, base, global nv)."""
+def balanced_ranges(offsets, nparts: int) -> list[int]:
+    """The reference's edge-balanced vertex ranges (option -b): balanceEdges, distgraph.cpp:22-66.
+
+    The reference walks the first nv offsets once: bin p takes vertices until the entries it
+    has SEEN reach ne // P — where vertex m is charged offsets[m] - offsets[m-1], i.e. the row of
+    vertex m-1 (its loop reads offsets[m], not offsets[m+1]) — and the vertex that fills the bin
+    already belongs to bin p+1 (distgraph.cpp:48-55).  Restated with one binary search per bin."""
+    off = np.asarray(offsets.cpu() if hasattr(offsets, "cpu") else offsets, dtype=np.int64)
+    nv = off.size - 1
+    cap = int(off[nv]) // nparts
+    seen = off[:nv]  # what the loop reads for m = 0 .. nv-1
+    parts, start, charged = [0], 0, 0
+    for _ in range(nparts - 1):
+        # first m >= start with seen[m] - charged >= cap; vertex m opens the next bin
+        m = start + int(np.searchsorted(seen[start:], charged + cap, side="left"))
+        if m >= nv:
+            parts.append(nv)
+            start = nv
+            continue
+        parts.append(m)
+        charged = int(seen[m])
+        start = m + 1
+    parts.append(nv)
+    return parts
+
+
+def read_vite(path: str, rank: int = 0, nparts: int = 1, balanced: bool = False) -> tuple[CSRGraph, int, int]:
+    """Returns (local rows as a CSRGraph with global tails, base, global nv).  ``balanced``
+    selects the reference's -b edge-balanced ranges (loadDistGraphMPIIOBalanced,
+    distgraph.cpp:205-337) instead of parts[p] = nv*p // P."""
     with open(path, "rb") as f:
         nv, ne = (int(x) for x in np.fromfile(f, dtype="<i8", count=2))
-        parts = partition_ranges(nv, nparts)
+        if balanced:
+            parts = balanced_ranges(np.fromfile(f, dtype="<i8", count=nv + 1), nparts)
+        else:
+            parts = partition_ranges(nv, nparts)
         base, bound = parts[rank], parts[rank + 1]
         f.seek(16 + base * 8)
         offsets = np.fromfile(f, dtype="<i8", count=bound - base + 1)

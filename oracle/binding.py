@@ -211,6 +211,14 @@ class Reference:
         offsets, tails, weights = _csr(offsets, tails, weights)
         return self.lib.ref_graph_create(offsets.size - 1, tails.size, offsets, tails, weights)
 
+    def balance_edges(self, path: str, nprocs: int) -> np.ndarray:
+        """balanceEdges (distgraph.cpp:22-66) on a Vite file: the -b vertex ranges."""
+        out = np.zeros(nprocs + 1, np.int64)
+        self.lib.ref_balance_edges.argtypes = [C.c_int, C.c_char_p, _i64p]
+        self.lib.ref_balance_edges.restype = None
+        self.lib.ref_balance_edges(nprocs, path.encode(), out)
+        return out
+
     def graph_load(self, path: str):
         return self.lib.ref_graph_load(path.encode())
 

@@ -76,6 +76,15 @@ void *ref_graph_load(const char *path) {
   return h;
 }
 
+// The reference's edge-balanced vertex ranges (-b): balanceEdges, distgraph.cpp:22-66.
+// mbins_out[nprocs + 1].
+void ref_balance_edges(int nprocs, const char *path, int64_t *mbins_out) {
+  std::string fn(path);
+  std::vector<GraphElem> mbins(nprocs + 1, 0);
+  balanceEdges(nprocs, fn, mbins);
+  for (int i = 0; i <= nprocs; i++) mbins_out[i] = mbins[i];
+}
+
 void ref_graph_destroy(void *hp) {
   RefGraph *h = static_cast<RefGraph *>(hp);
   delete h->dg;

@@ -39,5 +39,26 @@ def main():
         print(f"{name}: nv={o.size - 1} ne={t.size} iters={p.iters} q={p.q:.12f} levels={len(run.level_q)}")
 
 
+def balance_fixture():
+    """-b vertex ranges of the reference (balanceEdges, distgraph.cpp:22-66) for a few graphs."""
+    import tempfile
+    from cuvite_b200 import graphgen as gg, vite_io
+    R = Reference()
+    out = os.path.dirname(os.path.abspath(__file__))
+    cases = {"rmat12": gg.rmat(12, seed=2), "er3k": gg.erdos_renyi(3000, 8.0, seed=1),
+             "pl5k": gg.power_law(5000, 40000, seed=4), "ring6x5": gg.ring_of_cliques(6, 5)}
+    data = {}
+    with tempfile.TemporaryDirectory() as d:
+        for name, g in cases.items():
+            f = os.path.join(d, name + ".bin")
+            vite_io.write_vite(f, g)
+            data[name + "_offsets"] = g.offsets.numpy()
+            for P in (1, 2, 3, 4, 7, 8, 16, 64):
+                data[f"{name}_P{P}"] = R.balance_edges(f, P)
+    np.savez_compressed(os.path.join(out, "balance.npz"), **data)
+    print("balance.npz:", len(data), "arrays")
+
+
 if __name__ == "__main__":
+    balance_fixture()
     main()

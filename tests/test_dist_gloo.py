@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, name, exchange, ret):
+def _worker(rank, world, port, name, exchange, ret, balanced=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -26,12 +26,13 @@ def _worker(rank, world, port, name, exchange, ret):
     g = np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz"))
     o, t, w = g["offsets"], g["tails"].astype(np.int64), g["weights"]
     nv = o.size - 1
-    parts = partition_ranges(nv, world)
+    from cuvite_b200.vite_io import balanced_ranges
+    parts = balanced_ranges(o, world) if balanced else partition_ranges(nv, world)
     b0, b1 = parts[rank], parts[rank + 1]
     orc = Oracle()
     orc.set_num_threads(1)
     eng = OracleEngine(orc).upload(o[b0:b1 + 1] - o[b0], t[o[b0]:o[b1]], w[o[b0]:o[b1]], base=b0, nv_global=nv)
-    dl = DistLouvain(eng, rank, world, nv, exchange=exchange)
+    dl = DistLouvain(eng, rank, world, nv, exchange=exchange, parts=parts if balanced else None)
     q, iters = dl.run_phase()
     past = eng.tensor("labels_past").numpy()
     ok = (iters == int(g["iters"]) and abs(q - float(g["q"])) < 1e-12 and np.array_equal(past, g["cvect"][b0:b1]))
@@ -48,6 +49,16 @@ def test_distributed_phase_equals_one_rank_reference(oracle, world, name, exchan
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, name, exchange, ret), nprocs=world, join=True)
     assert len(ret) == world
+    for r in range(world):
+        assert ret[r][0], f"rank {r}: {ret[r]}"
+
+
+def test_distributed_phase_on_edge_balanced_ranges(oracle):
+    """The reference's -b ranges (uneven vertex counts, hub30k puts the hub rows on rank 0)."""
+    world, name = 3, "hub30k"
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, 29877, name, "labels", ret, True), nprocs=world, join=True)
     for r in range(world):
         assert ret[r][0], f"rank {r}: {ret[r]}"
 
