@@ -80,10 +80,15 @@ class DistLouvain:
             return
         if self.even:
             dist.all_gather_into_tensor(global_t, local_t.contiguous(), group=self.group)
-        else:  # uneven ranges (nv not divisible by P): one broadcast per owner
-            global_t[self.base:self.bound].copy_(local_t)
+        else:  # uneven ranges (coarsened levels, -b ranges): ONE all-gather of max-size chunks, then unpack
+            m = max(self.parts[p + 1] - self.parts[p] for p in range(self.world))
+            pad = torch.empty(m, dtype=local_t.dtype, device=local_t.device)
+            pad[:local_t.numel()].copy_(local_t)
+            buf = torch.empty(self.world * m, dtype=local_t.dtype, device=local_t.device)
+            dist.all_gather_into_tensor(buf, pad, group=self.group)
             for p in range(self.world):
-                dist.broadcast(global_t[self.parts[p]:self.parts[p + 1]], src=p, group=self.group)
+                a, b = self.parts[p], self.parts[p + 1]
+                global_t[a:b].copy_(buf[p * m:p * m + (b - a)])
 
     def _all_reduce(self, t: torch.Tensor, op=dist.ReduceOp.SUM):
         if self.world > 1:

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--scale", type=int, default=20)
     ap.add_argument("--permute", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-warmup", action="store_true", help="skip the untimed warm-up runs (large scales)")
     a = ap.parse_args()
     from cuvite_b200.dist import DistLouvain, init_process_group, load_partition
     from cuvite_b200.engine import GpuGraph, set_gpuDevices
@@ -43,9 +44,10 @@ def main():
     load_partition(gpu, g, rank, world)
     nv, ne = g.nv, g.ne
     dl = DistLouvain(gpu, rank, world, nv)
-    dl.run()  # warm-up (NCCL channels, allocator) on the same input
-    load_partition(gpu, g, rank, world)
-    dl = DistLouvain(gpu, rank, world, nv)
+    if not a.no_warmup:
+        dl.run()  # warm-up (NCCL channels, allocator) on the same input
+        load_partition(gpu, g, rank, world)
+        dl = DistLouvain(gpu, rank, world, nv)
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -61,8 +63,9 @@ def main():
     if rank == 0 and not a.no_check:
         one = GpuGraph(stream=side.cuda_stream)
         one.upload_device(g.offsets, g.tails, g.weights)
-        one.run()  # warm-up
-        one.upload_device(g.offsets, g.tails, g.weights)
+        if not a.no_warmup:
+            one.run()  # warm-up
+            one.upload_device(g.offsets, g.tails, g.weights)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         q1, i1, n1, c1 = one.run()
