@@ -12,6 +12,7 @@
 // One rank per process without MPI peers (nprocs == 1): the multi-GPU resident path is
 // cuvite_b200/dist.py over NCCL; an MPI multi-rank run keeps the per-iteration plugin
 // (adapter.cpp).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -52,11 +53,19 @@ GraphWeight distLouvainMethod(const int me, const int nprocs, const DistGraph &d
   iters = 0;
   if (nv <= 0) return lower;
   cvb_engine *e = gpu_graph.engine();
+  const bool timing = std::getenv("CVB_ADAPTER_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   if (cvb_graph_upload_host(e, nv, dg.getBase(me), dg.getTotalNumVertices(), g.edgeListIndexes.data(),
                             g.edgeList.data(), nullptr, nullptr) != CVB_OK)
     die_resident("distLouvainMethod/upload");
+  const double t1 = now();
   double q = lower;
   if (cvb_phase_run(e, lower, thresh, 0, &q, &iters) != CVB_OK) die_resident("distLouvainMethod/phase");
+  const double t2 = now();
   if (cvb_get_labels(e, CVB_LABELS_PAST, cvect.data()) != CVB_OK) die_resident("distLouvainMethod/labels");
+  if (timing)
+    std::printf("cuvite_b200 resident phase: nv=%lld entries=%lld upload %.4f s, phase %.4f s (%d iterations), labels %.4f s\n",
+                (long long)nv, (long long)g.getNumEdges(), t1 - t0, t2 - t1, iters, now() - t2);
   return q;
 }

@@ -50,6 +50,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=int, default=20)
     ap.add_argument("--threads", type=int, default=os.cpu_count())
+    ap.add_argument("--only", default="", help="comma-separated subset of the CLI binaries to run")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -63,9 +64,11 @@ def main():
         f = os.path.join(d, "g.bin")
         vite_io.write_vite(f, g)
         for tag in ("gc_gpu64", "gc_gpu_dropin", "gc_gpu_resident", "gc_cpu64"):
+            if a.only and tag not in a.only.split(","):
+                continue
             exe = os.path.join(ref, tag)
             out[tag] = run_cli(exe, f, a.threads) if os.path.exists(exe) else {"unavailable": True}
-    ks = out["gc_gpu64"].get("kernel_s_per_iteration")
+    ks = out.get("gc_gpu64", {}).get("kernel_s_per_iteration")
     if ks:
         n0 = out["gc_gpu64"]["levels"][0][3] if out["gc_gpu64"]["levels"] else len(ks)
         lvl0 = ks[:n0]  # level 0 runs on the full graph
