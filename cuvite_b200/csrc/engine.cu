@@ -161,12 +161,14 @@ struct cvb_engine {
   DevBuf<uint64_t> pair_keys;
   DevBuf<unsigned char> pair_w;
   int64_t pair_count = 0;
-  // The global tables of the big vertices are processed in batches that share ONE arena small
-  // enough to stay L2-resident (insert -> eval -> next batch reuses the same lines), instead of
-  // one table per vertex spread over gigabytes of HBM.
+  // The global tables of the big vertices are processed in batches that share ONE arena about
+  // the size of L2 (insert -> eval -> the next batch reuses the same lines), instead of one
+  // table per vertex spread over gigabytes of HBM (3 GB at R-MAT scale 24).  Measured: the
+  // arena bounds memory but buys little time (scale 24: 7.6 ms/sweep at 64 MB and unbatched,
+  // 7.85 at 32 MB where batches stop filling the GPU) — the insert is bound by L2 atomics.
   struct GiantBatch { int64_t chunk_lo, chunk_hi, piece_lo, piece_hi, slot_base; };
   std::vector<GiantBatch> giant_batches;
-  int64_t giant_arena_slots = 4 << 20;  // 32 MB of 8-byte slots; CVB_GIANT_ARENA_MB overrides
+  int64_t giant_arena_slots = 16 << 20;  // 128 MB of 8-byte slots (about one L2); CVB_GIANT_ARENA_MB overrides
   bool use_tma = false;        // CVB_TMA=1: cp.async.bulk + mbarrier staging of tails/weights tiles
   bool use_cluster = false;    // CVB_CLUSTER=1: DSMEM cluster kernels for 8193..65536
   bool giant_direct = false;   // CVB_GIANT_DIRECT=1: giant entries go straight to the global tables
