@@ -171,6 +171,9 @@ struct cvb_engine {
   int64_t giant_arena_slots = 16 << 20;  // 128 MB of 8-byte slots (about one L2); CVB_GIANT_ARENA_MB overrides
   bool use_tma = false;        // CVB_TMA=1: cp.async.bulk + mbarrier staging of tails/weights tiles
   bool use_cluster = false;    // CVB_CLUSTER=1: DSMEM cluster kernels for 8193..65536
+  bool use_twopass = true;     // 8193..16384: two-pass shared-memory kernel (CVB_NO_TWOPASS=1: global tables)
+  // first degree class that goes through the global tables
+  int global_table_class() const { return use_cluster ? kClsGiant : (use_twopass ? kClsC4 : kClsC2); }
   bool giant_direct = false;   // CVB_GIANT_DIRECT=1: giant entries go straight to the global tables
   bool use_first_sweep = true; // cvb env CVB_NO_FIRST_SWEEP=1 disables the singleton fast path
   bool rows_simple = false;    // every row holds each tail at most once (ascending)
@@ -401,7 +404,18 @@ int launch_sweep_u32(cvb_engine *e) {
   // them; CVB_CLUSTER=1 routes 8193..65536 to thread-block clusters with the table in
   // distributed shared memory (correct, but DSMEM moves ~32 B per 4-byte atomic and
   // measured slower on B200 — DESIGN.md section 5).
-  const int gcls = e->use_cluster ? kClsGiant : kClsC2;
+  const int gcls = e->global_table_class();
+  if (!e->use_cluster && e->use_twopass && (n = cnt(kClsC2)) > 0) {
+    constexpr int kTwoPassSmem = 16384 * 8;
+    static bool twopass_configured = false;
+    if (!twopass_configured) {
+      CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_twopass, cudaFuncAttributeMaxDynamicSharedMemorySize, kTwoPassSmem));
+      twopass_configured = true;
+    }
+    const int grid = static_cast<int>(n < e->num_sms ? n : e->num_sms);
+    k_sweep_u32_twopass<<<grid, 1024, kTwoPassSmem, e->aux[1]>>>(p, lst(kClsC2), static_cast<int>(n));
+    e->launches++;
+  }
   if (e->use_cluster) {
     if ((n = cnt(kClsC8)) > 0) CVB_TRY(launch_cluster<8>(e, e->aux[1], p, lst(kClsC8), n));
     if ((n = cnt(kClsC4)) > 0) CVB_TRY(launch_cluster<4>(e, e->aux[1], p, lst(kClsC4), n));
@@ -579,7 +593,7 @@ int post_graph(cvb_engine *e) {
       k_giant_chunk_owner<<<static_cast<int>(nbig), 64, 0, st>>>(e->big_layout.p, (int)nbig, e->big_owner.p);
       e->launches++;
     }
-    const int gcls = e->use_cluster ? kClsGiant : kClsC2;
+    const int gcls = e->global_table_class();
     const int64_t ngiant = e->class_start[kClsGiant + 1] - e->class_start[gcls];  // global-table vertices
     if (ngiant > 0) {
       CVB_TRY(e->giant_layout.ensure(2 * (ngiant + 1)));
@@ -718,6 +732,7 @@ cvb_engine *cvb_create(void *stream) {
     if (mb > 0) e->giant_arena_slots = static_cast<int64_t>(mb) << 17;
   }
   if (const char *s = getenv("CVB_CLUSTER")) e->use_cluster = (s[0] == '1');
+  if (const char *s = getenv("CVB_NO_TWOPASS")) e->use_twopass = (s[0] != '1');
   if (const char *s = getenv("CVB_TMA")) e->use_tma = (s[0] == '1');
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) e->num_sms = sms;

@@ -846,6 +846,152 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_u32_cluster(SweepU32Params p,
 }
 
 // ---------------------------------------------------------------------------
+// deg 8193..16384: one block per vertex, the adjacency is read TWICE and each pass
+// accumulates the neighbour communities of one half of the key space (a mixing
+// hash of the community id picks the half) in a 16384-slot shared-memory table.
+// The second read of the row (<= 128 KB) comes from L2; no global table, no L2
+// atomic, no second kernel.  A table can never overflow: a row has at most 16384
+// entries, hence at most 16384 distinct communities in total.
+// After each pass the table is scanned (16 slots per thread), every community
+// found is evaluated and its slot freed.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t key_half(uint32_t key) {
+  uint32_t m = (key & kLabelMask) * 0xC2B2AE35u;
+  m ^= m >> 15;
+  m *= 0x27D4EB2Fu;
+  return m >> 31;
+}
+
+__global__ void __launch_bounds__(1024, 1) k_sweep_u32_twopass(SweepU32Params p, const vid_t *__restrict__ list, int n) {
+  constexpr int TPB = 1024, KC = 4, CAP = 16384, kLog2Cap = 14;
+  constexpr uint32_t capb = CAP * 4u, maskb = (CAP - 1u) << 2;
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  __shared__ double red_g[32];
+  __shared__ uint32_t red_id[32];
+  __shared__ uint32_t meta[4];
+  uint32_t *keys = smem_u32, *wts = smem_u32 + CAP;
+  const uint32_t kaddr = smem_addr(keys);
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = threadIdx.x >> 5;
+  const int tid = threadIdx.x;
+  for (int s = tid; s < CAP; s += TPB) {
+    keys[s] = kEmptyKeyU;
+    wts[s] = 0u;
+  }
+  if (tid < 4) meta[tid] = 0u;
+  __syncthreads();
+  for (int64_t item = blockIdx.x; item < n; item += gridDim.x) {
+    const vid_t v = list[item];
+    const eid_t e0 = p.offsets[v];
+    const int deg = static_cast<int>(p.offsets[v + 1] - e0);
+    const vid_t self = v + p.base;
+    const uint2 me = p.packed[self];
+    const uint32_t cc = me.x & kLabelMask;
+    const double vd = p.vdeg[v];
+    const double ax = static_cast<double>(me.y) - vd;
+    const vid_t *__restrict__ row_tails = p.tails + e0;
+    const uint32_t *__restrict__ row_weights = p.weights + e0;
+    double g = -1.0, eix = 0.0, counter0 = 0.0;
+    uint32_t id = kLabelMask;
+    for (uint32_t half = 0; half < 2u; ++half) {
+      uint32_t ownsum = 0u, selfsum = 0u;
+      for (int i0 = 0; i0 < deg; i0 += TPB * KC) {
+        uint32_t key[KC], w[KC], slb[KC];
+        vid_t tail[KC];
+        uint32_t validm = 0u, active = 0u;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const int i = i0 + tid + k * TPB;
+          tail[k] = self;
+          w[k] = 0u;
+          if (i < deg) {
+            // first pass: default loads leave the row in L2 for the second pass, which streams it out
+            tail[k] = half ? __ldcs(&row_tails[i]) : __ldg(&row_tails[i]);
+            w[k] = half ? __ldcs(&row_weights[i]) : __ldg(&row_weights[i]);
+            validm |= 1u << k;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const uint2 pk = p.packed[tail[k]];
+          const bool valid = (validm >> k) & 1u;
+          key[k] = valid ? pk.x : kEmptyKeyU;
+          const bool own = (key[k] & kLabelMask) == cc;
+          ownsum += own ? w[k] : 0u;
+          selfsum += (valid && tail[k] == self) ? w[k] : 0u;
+          active |= (valid && !own && key_half(key[k]) == half) ? (1u << k) : 0u;
+        }
+        if (__any_sync(0xffffffffu, active != 0u))
+          (void)table_insert_chunk<KC>(kaddr, capb, key, w, active, kLog2Cap, maskb, slb);
+      }
+      if (half == 0u) {  // own-community and self-loop weight: counted once
+        const uint32_t c0u = __reduce_add_sync(0xffffffffu, ownsum);
+        const uint32_t slu = __reduce_add_sync(0xffffffffu, selfsum);
+        if (lane == 0) {
+          if (c0u) atomicAdd(&meta[2], c0u);
+          if (slu) atomicAdd(&meta[1], slu);
+        }
+      }
+      __syncthreads();
+      if (half == 0u) {
+        counter0 = static_cast<double>(meta[2]);
+        eix = counter0 - static_cast<double>(meta[1]);
+      }
+      // evaluate and free this half's table: 16 slots per thread, 4 records in flight
+#pragma unroll
+      for (int j0 = 0; j0 < CAP / TPB; j0 += 4) {
+        uint32_t rk[4], rw[4];
+        double ayv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a = kaddr + (static_cast<uint32_t>(tid + (j0 + j) * TPB) << 2);
+          rk[j] = lds_u32(a);
+          rw[j] = lds_u32(a + capb);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ayv[j] = 0.0;
+          if (rk[j] != kEmptyKeyU) {
+            ayv[j] = p.cdeg[rk[j] & kLabelMask];
+            const uint32_t a = kaddr + (static_cast<uint32_t>(tid + (j0 + j) * TPB) << 2);
+            sts_u32(a, kEmptyKeyU);
+            sts_u32(a + capb, 0u);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (rk[j] != kEmptyKeyU) {
+            const double g2 = modularity_gain(static_cast<double>(rw[j]), eix, vd, ayv[j], ax, p.constant);
+            if (better_u(g2, rk[j], g, id)) {
+              g = g2;
+              id = rk[j];
+            }
+          }
+      }
+      __syncthreads();  // the table is clean before the next pass / vertex inserts
+    }
+    double wg;
+    uint32_t wid = warp_argmax(g, id, &wg);
+    if (lane == 0) {
+      red_g[wib] = wg;
+      red_id[wib] = wid;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 1; i < TPB / 32; ++i)
+        if (better_u(red_g[i], red_id[i], wg, wid)) {
+          wg = red_g[i];
+          wid = red_id[i];
+        }
+      commit_vertex_u32(p, v, me.x, wg, wid, vd, counter0);
+      meta[1] = 0u;
+      meta[2] = 0u;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
 // deg > 8192: tables in global memory, three kernels.
 //   k_sweep_u32_giant_insert : blocks take 4096-entry chunks of giant
 //       adjacencies (chunk -> vertex by binary search in chunk_start) and

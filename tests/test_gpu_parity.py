@@ -300,15 +300,19 @@ def test_tma_staged_variant_matches_reference(monkeypatch):
     gpu.close()
 
 
-@pytest.mark.parametrize("cluster,arena_mb", [(False, 0), (True, 0), (False, 1)])
-def test_true_giant_hub_matches_oracle(oracle, cluster, arena_mb, monkeypatch):
-    """Vertices above 8192 entries: global-table path (default; arena_mb=1 forces one batch per
-    big vertex through the shared table arena) and the thread-block-cluster /
-    distributed-shared-memory path (CVB_CLUSTER=1), incl. one vertex above 65536 entries."""
+@pytest.mark.parametrize("cluster,arena_mb,twopass", [(False, 0, True), (True, 0, True), (False, 1, True),
+                                                      (False, 0, False)])
+def test_true_giant_hub_matches_oracle(oracle, cluster, arena_mb, twopass, monkeypatch):
+    """Vertices above 8192 entries: the two-pass shared-memory kernel for 8193..16384 (default;
+    twopass=False sends that class through the global tables too), the global-table path above
+    (arena_mb=1 forces one batch per big vertex through the shared table arena) and the
+    thread-block-cluster / distributed-shared-memory path (CVB_CLUSTER=1), incl. one vertex
+    above 65536 entries."""
     import torch
     from cuvite_b200 import graphgen as gg
     from cuvite_b200.engine import GpuGraph
     monkeypatch.setenv("CVB_CLUSTER", "1" if cluster else "0")
+    monkeypatch.setenv("CVB_NO_TWOPASS", "0" if twopass else "1")
     if arena_mb:
         monkeypatch.setenv("CVB_GIANT_ARENA_MB", str(arena_mb))
     gpu = GpuGraph()
@@ -317,7 +321,7 @@ def test_true_giant_hub_matches_oracle(oracle, cluster, arena_mb, monkeypatch):
     src = np.repeat(np.arange(nv, dtype=np.int64), np.diff(bg.offsets.numpy()))
     dst = bg.tails.numpy()
     es, ed = [src], [dst]
-    for hub, deg in ((0, nv - 1), (1, 40000), (2, 20000), (3, 10000)):
+    for hub, deg in ((0, nv - 1), (1, 40000), (2, 20000), (3, 10000), (4, 16000), (5, 8300)):
         es.append(np.full(deg, hub, np.int64))
         ed.append((np.arange(deg, dtype=np.int64) * 7919 + 11 * hub + 13) % nv)
     g = gg.csr_from_pairs(nv, torch.from_numpy(np.concatenate(es)), torch.from_numpy(np.concatenate(ed)))
