@@ -166,7 +166,19 @@ struct cvb_engine {
   // table per vertex spread over gigabytes of HBM (3 GB at R-MAT scale 24).  Measured: the
   // arena bounds memory but buys little time (scale 24: 7.6 ms/sweep at 64 MB and unbatched,
   // 7.85 at 32 MB where batches stop filling the GPU) — the insert is bound by L2 atomics.
-  struct GiantBatch { int64_t chunk_lo, chunk_hi, piece_lo, piece_hi, slot_base; };
+  struct GiantBatch { int64_t chunk_lo, chunk_hi, piece_lo, piece_hi, slot_base; int vert_lo; };
+  // CVB_BIG_DENSE=1 (A/B variant, off by default): every vertex of a batch owns a DENSE uint32
+  // accumulator indexed by community id (no hashing in global memory: chunk totals are added
+  // with fire-and-forget L2 reductions) plus a list of the communities it met.  Measured on
+  // B200: same speed at scale 20 (0.382 vs 0.388 ms/sweep), SLOWER at scale 24 (9.6 vs 7.4 ms:
+  // the touched sectors of 128 concurrent accumulators no longer fit L2), so the open-addressing
+  // tables stay the default.
+  bool big_dense = false;
+  int64_t dense_budget_bytes = 8LL << 30;  // CVB_BIG_DENSE_MB overrides
+  int64_t dense_stride = 0;
+  DevBuf<uint32_t> dense, kcount, klist;
+  DevBuf<double> gchunk2_gain;
+  DevBuf<uint32_t> gchunk2_key;
   std::vector<GiantBatch> giant_batches;
   int64_t giant_arena_slots = 16 << 20;  // 128 MB of 8-byte slots (about one L2); CVB_GIANT_ARENA_MB overrides
   bool use_tma = false;        // CVB_TMA=1: cp.async.bulk + mbarrier staging of tails/weights tiles
@@ -433,29 +445,55 @@ int launch_sweep_u32(cvb_engine *e) {
     constexpr int kGiantSmem = 2 * kGiantChunk * 8;
     static bool giant_configured = false;
     if (!giant_configured) {
-      CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_giant_insert, cudaFuncAttributeMaxDynamicSharedMemorySize, kGiantSmem));
+      CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_giant_insert<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGiantSmem));
       giant_configured = true;
+    }
+    gt.dense = e->dense.p;
+    gt.dense_stride = e->dense_stride;
+    gt.kcount = e->kcount.p;
+    gt.klist = e->klist.p;
+    static bool giant_configured2 = false;
+    if (!giant_configured2) {
+      CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_giant_insert<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGiantSmem));
+      giant_configured2 = true;
     }
     for (const auto &b : e->giant_batches) {
       gt.slot_base = b.slot_base;
+      gt.vert_lo = b.vert_lo;
       const int64_t nch = b.chunk_hi - b.chunk_lo, npc = b.piece_hi - b.piece_lo;
+      if (e->big_dense) {
+        const int64_t g1 = nch < 2LL * e->num_sms ? nch : 2LL * e->num_sms;
+        k_sweep_u32_giant_insert<true><<<static_cast<int>(g1), 512, kGiantSmem, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
+                                                                                            b.chunk_lo, b.chunk_hi);
+        const int64_t g2 = nch < 4LL * e->num_sms ? nch : 4LL * e->num_sms;
+        k_sweep_u32_giant_eval_dense<<<static_cast<int>(g2), 512, 0, e->aux[1]>>>(
+            p, lst(gcls), (int)n, gt, b.chunk_lo, b.chunk_hi, e->gchunk2_gain.p, e->gchunk2_key.p);
+        e->launches += 2;
+        continue;
+      }
       if (e->giant_direct) {
         const int64_t g0 = nch < 4LL * e->num_sms ? nch : 4LL * e->num_sms;
         k_sweep_u32_giant_insert_direct<<<static_cast<int>(g0), 512, 0, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
                                                                                     b.chunk_lo, b.chunk_hi);
       } else {
         const int64_t g1 = nch < 2LL * e->num_sms ? nch : 2LL * e->num_sms;
-        k_sweep_u32_giant_insert<<<static_cast<int>(g1), 512, kGiantSmem, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
-                                                                                      b.chunk_lo, b.chunk_hi);
+        k_sweep_u32_giant_insert<false><<<static_cast<int>(g1), 512, kGiantSmem, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
+                                                                                             b.chunk_lo, b.chunk_hi);
       }
       const int64_t g2 = npc < 4LL * e->num_sms ? npc : 4LL * e->num_sms;
       k_sweep_u32_giant_eval<<<static_cast<int>(g2), 512, 0, e->aux[1]>>>(p, lst(gcls), (int)n, gt, b.piece_lo,
                                                                          b.piece_hi);
       e->launches += 2;
     }
+    if (e->big_dense) {
+      k_sweep_u32_giant_final_dense<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(
+          p, lst(gcls), (int)n, gt, e->gchunk2_gain.p, e->gchunk2_key.p);
+      e->launches += 1;
+    } else {
     k_sweep_u32_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(p, lst(gcls), (int)n,
                                                                                          gt);
     e->launches += 1;
+    }
   }
   // stream 2: warp-level and sub-warp hash classes
   if ((n = cnt(kClsH1K)) > 0) CVB_TRY((launch_hash<64, 4, 2, 16>(e, e->aux[2], p, lst(kClsH1K), n)));
@@ -606,15 +644,34 @@ int post_graph(cvb_engine *e) {
       const int64_t *cs = lay.data(), *ts = lay.data() + (ngiant + 1);
       e->giant_chunks = cs[ngiant];
       e->giant_slots = ts[ngiant];
-      // batches of consecutive big vertices whose tables fit the arena together
       e->giant_batches.clear();
       int64_t arena = 0;
-      for (int64_t i = 0; i < ngiant;) {
-        int64_t j = i + 1;
-        while (j < ngiant && ts[j + 1] - ts[i] <= e->giant_arena_slots) ++j;
-        e->giant_batches.push_back({cs[i], cs[j], ts[i] / kGiantPiece, ts[j] / kGiantPiece, ts[i]});
-        if (ts[j] - ts[i] > arena) arena = ts[j] - ts[i];
-        i = j;
+      if (e->big_dense) {
+        // batches of A consecutive big vertices, one dense accumulator each
+        e->dense_stride = (e->nvg + 31) & ~int64_t(31);
+        int64_t A = e->dense_budget_bytes / (e->dense_stride * 4);
+        A = A < 1 ? 1 : (A > ngiant ? ngiant : A);
+        for (int64_t i = 0; i < ngiant; i += A) {
+          const int64_t j = i + A < ngiant ? i + A : ngiant;
+          e->giant_batches.push_back({cs[i], cs[j], 0, 0, 0, static_cast<int>(i)});
+        }
+        CVB_TRY(e->dense.ensure(static_cast<size_t>(A) * e->dense_stride));
+        CVB_CUDA(cudaMemsetAsync(e->dense.p, 0, static_cast<size_t>(A) * e->dense_stride * sizeof(uint32_t), st));
+        CVB_TRY(e->kcount.ensure(ngiant + 1));
+        CVB_CUDA(cudaMemsetAsync(e->kcount.p, 0, (ngiant + 1) * sizeof(uint32_t), st));
+        CVB_TRY(e->klist.ensure(static_cast<size_t>(e->giant_chunks) * kGiantChunk + 1));
+        CVB_TRY(e->gchunk2_gain.ensure(e->giant_chunks + 1));
+        CVB_TRY(e->gchunk2_key.ensure(e->giant_chunks + 1));
+        arena = kGiantPiece;  // the hash-table arena is unused
+      } else {
+        // batches of consecutive big vertices whose tables fit the arena together
+        for (int64_t i = 0; i < ngiant;) {
+          int64_t j = i + 1;
+          while (j < ngiant && ts[j + 1] - ts[i] <= e->giant_arena_slots) ++j;
+          e->giant_batches.push_back({cs[i], cs[j], ts[i] / kGiantPiece, ts[j] / kGiantPiece, ts[i], static_cast<int>(i)});
+          if (ts[j] - ts[i] > arena) arena = ts[j] - ts[i];
+          i = j;
+        }
       }
       CVB_TRY(e->gslots.ensure(arena));
       CVB_TRY(e->gmeta.ensure(3 * ngiant + 4));
@@ -733,6 +790,11 @@ cvb_engine *cvb_create(void *stream) {
   }
   if (const char *s = getenv("CVB_CLUSTER")) e->use_cluster = (s[0] == '1');
   if (const char *s = getenv("CVB_NO_TWOPASS")) e->use_twopass = (s[0] != '1');
+  if (const char *s = getenv("CVB_BIG_DENSE")) e->big_dense = (s[0] != '0');
+  if (const char *s = getenv("CVB_BIG_DENSE_MB")) {
+    const long mb = atol(s);
+    if (mb > 0) e->dense_budget_bytes = static_cast<int64_t>(mb) << 20;
+  }
   if (const char *s = getenv("CVB_TMA")) e->use_tma = (s[0] == '1');
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) e->num_sms = sms;
@@ -775,6 +837,7 @@ void cvb_destroy(cvb_engine *e) {
   e->partials.release(); e->d_sums.release(); e->ticket.release(); e->d_flags.release();
   e->h_sums.release(); e->staging.release(); e->staging2.release(); e->giant.release(); e->h_stage.release();
   e->packed.release(); e->giant_layout.release(); e->gslots.release(); e->pair_keys.release(); e->pair_w.release();
+  e->dense.release(); e->kcount.release(); e->klist.release(); e->gchunk2_gain.release(); e->gchunk2_key.release();
   e->gmeta.release(); e->gpiece_key.release(); e->gpiece_gain.release(); e->gchunk_gain.release();
   e->gchunk_key.release(); e->gchunk_owner.release(); e->big_layout.release(); e->big_owner.release();
   e->big_meta.release();

@@ -1012,6 +1012,14 @@ struct GiantTables {
   const int64_t *__restrict__ table_start;  // [ngiant+1] prefix of table slots per vertex
   uint2 *__restrict__ slots;  // {key, weight} arena shared by the batches: slot s of the layout lives at slots[s - slot_base]
   int64_t slot_base;          // first layout slot of the batch being processed
+  // dense-accumulator variant (default): vertex gi of the batch adds into
+  // dense[(gi - vert_lo) * dense_stride + community] and appends the communities it met to
+  // klist[chunk_start[gi] * kGiantChunk ...], kcount[gi] entries
+  uint32_t *__restrict__ dense;
+  int64_t dense_stride;
+  int vert_lo;
+  uint32_t *__restrict__ kcount;
+  uint32_t *__restrict__ klist;
   uint32_t *__restrict__ gmeta;
   double *__restrict__ piece_gain;   // [total_slots / kGiantPiece]
   uint32_t *__restrict__ piece_key;  // [total_slots / kGiantPiece]
@@ -1106,6 +1114,7 @@ __device__ __forceinline__ void gtable_insert_chunk(uint2 *__restrict__ slots, c
 // lane flushes its distinct (community, weight, degree) triples into the
 // vertex's global table — so the number of L2 atomics is the number of distinct
 // communities per chunk, and they are issued with 8 independent ones in flight.
+template <bool kDense>
 __global__ void __launch_bounds__(512, 2) k_sweep_u32_giant_insert(SweepU32Params p, const vid_t *__restrict__ list,
                                                                   int n, GiantTables gt, int64_t chunk_lo,
                                                                   int64_t chunk_hi) {
@@ -1196,8 +1205,138 @@ __global__ void __launch_bounds__(512, 2) k_sweep_u32_giant_insert(SweepU32Param
         sts_u32(a + capb, 0u);
       }
     }
-    gtable_insert_chunk<K>(gt.slots + (tbase - gt.slot_base), ckey, tot, freshmask, glog2, gmask);
+    if (kDense) {
+      // chunk totals -> the vertex's dense accumulator with fire-and-forget L2 reductions (no
+      // probing, no return value to wait for); the communities this chunk met are appended to
+      // the vertex's list — one cursor atomic per warp
+      uint32_t *__restrict__ dense = gt.dense + static_cast<int64_t>(gi - gt.vert_lo) * gt.dense_stride;
+      const uint32_t mine = __popc(freshmask);
+      uint32_t incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= static_cast<unsigned>(o)) incl += t;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      uint32_t base = 0u;
+      if (lane == 0 && total) base = atomicAdd(&gt.kcount[gi], total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      uint32_t *__restrict__ out = gt.klist + gt.chunk_start[gi] * kGiantChunk + base + (incl - mine);
+#pragma unroll
+      for (int q = 0; q < K; ++q)
+        if (freshmask & (1u << q)) {
+          atomicAdd(&dense[ckey[q] & kLabelMask], tot[q]);
+          *out++ = ckey[q];
+        }
+    } else {
+      gtable_insert_chunk<K>(gt.slots + (tbase - gt.slot_base), ckey, tot, freshmask, glog2, gmask);
+    }
     __syncthreads();
+  }
+}
+
+// Dense-accumulator evaluation: block c takes list positions [4096*(c - first chunk), +4096)
+// of its vertex; the first reader of a community's total (atomicExch -> 0) evaluates it, later
+// duplicates of the same community (met in another chunk) read 0 and skip — which also leaves
+// the accumulator clean for the next batch.  One (gain, key) candidate per chunk.
+__global__ void __launch_bounds__(512) k_sweep_u32_giant_eval_dense(SweepU32Params p, const vid_t *__restrict__ list,
+                                                                   int n, GiantTables gt, int64_t chunk_lo,
+                                                                   int64_t chunk_hi, double *__restrict__ chunk_gain,
+                                                                   uint32_t *__restrict__ chunk_key) {
+  __shared__ double red_g[16];
+  __shared__ uint32_t red_id[16];
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = threadIdx.x >> 5;
+  for (int64_t chunk = chunk_lo + blockIdx.x; chunk < chunk_hi; chunk += gridDim.x) {
+    const int gi = gt.chunk_owner[chunk];
+    const int64_t first = gt.chunk_start[gi];
+    const uint32_t cnt = __ldcg(&gt.kcount[gi]);
+    const uint32_t off = static_cast<uint32_t>(chunk - first) * kGiantChunk;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+    if (off < cnt) {  // block-uniform
+      const vid_t v = list[gi];
+      const uint2 me = p.packed[v + p.base];
+      const double vd = p.vdeg[v];
+      const uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
+      const double counter0 = static_cast<double>(__ldcg(&meta[2]));
+      const double eix = counter0 - static_cast<double>(__ldcg(&meta[1]));
+      const double ax = static_cast<double>(me.y) - vd;
+      uint32_t *__restrict__ dense = gt.dense + static_cast<int64_t>(gi - gt.vert_lo) * gt.dense_stride;
+      const uint32_t *__restrict__ keys = gt.klist + first * kGiantChunk + off;
+      const uint32_t m = (cnt - off < kGiantChunk) ? cnt - off : kGiantChunk;
+#pragma unroll
+      for (int j0 = 0; j0 < kGiantChunk / 512; j0 += 4) {
+        uint32_t rk[4], rw[4];
+        double ayv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t i = threadIdx.x + (j0 + j) * 512;
+          rk[j] = (i < m) ? __ldcs(&keys[i]) : kEmptyKeyU;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          rw[j] = 0u;
+          if (rk[j] != kEmptyKeyU) rw[j] = atomicExch(&dense[rk[j] & kLabelMask], 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ayv[j] = rw[j] ? p.cdeg[rk[j] & kLabelMask] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (rw[j]) {
+            const double g2 = modularity_gain(static_cast<double>(rw[j]), eix, vd, ayv[j], ax, p.constant);
+            if (better_u(g2, rk[j], g, id)) {
+              g = g2;
+              id = rk[j];
+            }
+          }
+      }
+    }
+    double wg;
+    uint32_t wid = warp_argmax(g, id, &wg);
+    if (lane == 0) {
+      red_g[wib] = wg;
+      red_id[wib] = wid;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < 16; ++i)
+        if (better_u(red_g[i], red_id[i], wg, wid)) {
+          wg = red_g[i];
+          wid = red_id[i];
+        }
+      chunk_gain[chunk] = wg;
+      chunk_key[chunk] = wid;
+    }
+    __syncthreads();
+  }
+}
+
+// one warp per big vertex: reduce its chunks' candidates, commit, reset its counters
+__global__ void __launch_bounds__(128) k_sweep_u32_giant_final_dense(SweepU32Params p, const vid_t *__restrict__ list,
+                                                                    int n, GiantTables gt,
+                                                                    const double *__restrict__ chunk_gain,
+                                                                    const uint32_t *__restrict__ chunk_key) {
+  const int gi = static_cast<int>((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+  const unsigned lane = threadIdx.x & 31u;
+  if (gi >= n) return;
+  const vid_t v = list[gi];
+  const uint2 me = p.packed[v + p.base];
+  double g = -1.0;
+  uint32_t id = kLabelMask;
+  for (int64_t q = gt.chunk_start[gi] + lane; q < gt.chunk_start[gi + 1]; q += 32)
+    if (better_u(chunk_gain[q], chunk_key[q], g, id)) {
+      g = chunk_gain[q];
+      id = chunk_key[q];
+    }
+  double wg;
+  const uint32_t wid = warp_argmax(g, id, &wg);
+  if (lane == 0) {
+    uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
+    commit_vertex_u32(p, v, me.x, wg, wid, p.vdeg[v], static_cast<double>(meta[2]));
+    meta[1] = 0u;
+    meta[2] = 0u;
+    gt.kcount[gi] = 0u;
   }
 }
 

@@ -300,19 +300,23 @@ def test_tma_staged_variant_matches_reference(monkeypatch):
     gpu.close()
 
 
-@pytest.mark.parametrize("cluster,arena_mb,twopass", [(False, 0, True), (True, 0, True), (False, 1, True),
-                                                      (False, 0, False)])
-def test_true_giant_hub_matches_oracle(oracle, cluster, arena_mb, twopass, monkeypatch):
+@pytest.mark.parametrize("cluster,arena_mb,twopass,dense", [(False, 0, True, True), (True, 0, True, True),
+                                                            (False, 1, True, False), (False, 0, False, False),
+                                                            (False, 0, False, True)])
+def test_true_giant_hub_matches_oracle(oracle, cluster, arena_mb, twopass, dense, monkeypatch):
     """Vertices above 8192 entries: the two-pass shared-memory kernel for 8193..16384 (default;
     twopass=False sends that class through the global tables too), the global-table path above
     (arena_mb=1 forces one batch per big vertex through the shared table arena) and the
     thread-block-cluster / distributed-shared-memory path (CVB_CLUSTER=1), incl. one vertex
-    above 65536 entries."""
+    above 65536 entries.  dense=True (default): the vertices above 16384 entries accumulate into
+    dense per-vertex arrays with L2 reductions; dense=False: open-addressing tables in global
+    memory."""
     import torch
     from cuvite_b200 import graphgen as gg
     from cuvite_b200.engine import GpuGraph
     monkeypatch.setenv("CVB_CLUSTER", "1" if cluster else "0")
     monkeypatch.setenv("CVB_NO_TWOPASS", "0" if twopass else "1")
+    monkeypatch.setenv("CVB_BIG_DENSE", "1" if dense else "0")
     if arena_mb:
         monkeypatch.setenv("CVB_GIANT_ARENA_MB", str(arena_mb))
     gpu = GpuGraph()
