@@ -275,6 +275,29 @@ def bench_single(args):
     csr = ne * 16 + (nv + 1) * 8 + nv * 8
     h2d_step = h2d + csr * csr_uploads / args.steps
 
+    # ---- the same through the OUTER boundary (adapter_resident.cpp's distLouvainMethod(.., GpuGraph&)): one
+    # ---- AoS upload from pinned host memory per phase, all sweeps on the device, cvect back to the host
+    def resident_phases(min_sweeps):
+        sweeps = phases = 0
+        while sweeps < min_sweeps:
+            gpu.upload_aos(o_pin, edges_p)
+            _, iters = gpu.phase_run(-1.0, 1e-6)
+            gpu.labels(0)
+            sweeps += iters
+            phases += 1
+        return sweeps, phases
+
+    resident_phases(1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res_sweeps, res_phases = resident_phases(args.steps)
+    torch.cuda.synchronize()
+    res_s = time.perf_counter() - t0
+    resident = {"value": (ne / 2) * res_sweeps / res_s, "unit": UNIT, "sweeps": res_sweeps,
+                "h2d_bytes_per_step": int(csr * res_phases / res_sweeps), "d2h_bytes_per_step": int(nv * 8 * res_phases / res_sweeps),
+                "api": "distLouvainMethod(.., GpuGraph&) on the resident engine: cvb_graph_upload_host (pinned AoS) + "
+                       "cvb_phase_run + cvb_get_labels per phase"}
+
     # ---- CPU baseline beside it (bounded sample: phase 0 of the same graph) -----
     cpu = None
     try:
@@ -319,7 +342,8 @@ def bench_single(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step),
                     "d2h_bytes_per_step": int(d2h),
-                    "api": "gpu_for_louvain_iteration + gpu_reduce_mod (plugin calls, pinned host buffers)"},
+                    "api": "gpu_for_louvain_iteration + gpu_reduce_mod (plugin calls, pinned host buffers)",
+                    "resident": resident},
             "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)
     gpu.close()
