@@ -197,11 +197,13 @@ class DistLouvain:
            reference's partition of the new graph, ``parts[p] = nc*p // P`` (rebuild.cpp:294-295);
         4. the owner merges what it received and emits its CSR rows (sorted by tail).
 
-        Returns (newid, nc): newid[i] = new vertex of old GLOBAL vertex i (replicated tensor)."""
+        Returns (newid, nc): newid[i] = new vertex of old GLOBAL vertex i (replicated tensor);
+        the all-gathered cvect of the level is left in ``self.last_cvect``."""
         e = self.e
         cv_local = tensor_of(e, "labels_past")
         cv_global = torch.empty(self.nvg, dtype=cv_local.dtype, device=cv_local.device)
         self._all_gather_rows(cv_global, cv_local)
+        self.last_cvect = cv_global
         newid, nc = e.renumber(cv_global)
         keys, w = e.contract_local(newid, nc)
         parts = partition_ranges(nc, self.world)
@@ -222,12 +224,21 @@ class DistLouvain:
         self._set_nv_global(nc)
         return newid, nc
 
-    def run(self, max_levels: int = 200, threshold: float = 1.0e-6):
+    def run(self, max_levels: int = 200, threshold: float = 1.0e-6, reference_numbering: bool = False):
         """The default phase loop of main.cpp:218-495 across ranks.  Returns (level_q,
         level_iters (cumulative, as the reference prints them), level_nv, comm) where
-        comm[i] is the final community of original GLOBAL vertex i (replicated tensor)."""
+        comm[i] is the final community of original GLOBAL vertex i (replicated tensor).
+
+        Community ids: by default the coarsening's own numbering (first appearance,
+        rebuild.cpp:72-85 — the numbering of the golden fixtures).  ``reference_numbering``
+        gives the ids main.cpp writes to ``<input>.communities``: at every level the cvect values
+        are replaced by their rank among the sorted distinct values ("ensure clusters are
+        contiguous", main.cpp:375-396) before composing (main.cpp:397-404) — including the
+        reference's quirk that this composition indexes level l's vertices (numbered by rebuild in
+        first-appearance order) with level l-1's sorted-rank ids, so beyond the first level the
+        dumped ids describe the reference's output, not necessarily the partition found."""
         level_q, level_iters, level_nv = [], [], []
-        comm, nv0 = None, self.nvg
+        comm, comm_ref, nv0 = None, None, self.nvg
         curr, prev, tot_iters, phase = -1.0, -1.0, 0, 0
         while True:
             nv = self.nvg
@@ -235,6 +246,12 @@ class DistLouvain:
             tot_iters += iters
             if (curr - prev) > threshold:  # main.cpp:361
                 newid, _ = self.coarsen()  # main.cpp:413
+                if reference_numbering:
+                    cv = self.last_cvect.long()
+                    ranks = torch.searchsorted(torch.unique(cv), cv)  # unique() returns the values sorted
+                    # NB main.cpp:402 indexes the level's cvect with the PREVIOUS level's sorted-rank ids
+                    # although the level's vertices carry rebuild's first-appearance ids; mirrored as is
+                    comm_ref = ranks if comm_ref is None else ranks[comm_ref]
                 comm = newid.clone() if comm is None else newid[comm.long()]  # main.cpp:401-404
             else:
                 break
@@ -246,9 +263,10 @@ class DistLouvain:
             phase += 1
             if phase == 200 or tot_iters > 10000:  # main.cpp:486
                 break
-        if comm is None:  # no level improved: every vertex is its own community
+        if comm is None:  # no level improved: main.cpp:196 leaves commAll at its initial -1
             comm = torch.arange(nv0, dtype=torch.int64)
-        return level_q, level_iters, level_nv, comm
+            comm_ref = torch.full((nv0,), -1, dtype=torch.int64)
+        return level_q, level_iters, level_nv, (comm_ref if reference_numbering else comm)
 
 
 def init_process_group(backend: str | None = None):

@@ -85,3 +85,13 @@ def slice_rows(g: CSRGraph, base: int, bound: int) -> CSRGraph:
     """Rows [base, bound) of an in-memory graph, offsets rebased, tails global."""
     e0, e1 = int(g.offsets[base]), int(g.offsets[bound])
     return CSRGraph(bound - base, g.offsets[base:bound + 1] - e0, g.tails[e0:e1], g.weights[e0:e1])
+
+
+def write_communities(path: str, comm) -> None:
+    """The reference's community dump (main.cpp:521-541): one community id per line, vertex order.
+    ``DistLouvain.run(reference_numbering=True)`` yields the ids main.cpp would write."""
+    a = np.asarray(comm.cpu() if hasattr(comm, "cpu") else comm, dtype=np.int64)
+    with open(path, "w") as f:
+        f.write("\n".join(map(str, a.tolist())))
+        if a.size:
+            f.write("\n")

@@ -103,6 +103,48 @@ def test_distributed_multilevel_run_equals_one_rank_reference(oracle, world, nam
         assert ret[r][0], f"rank {r}: {ret[r]}"
 
 
+def _communities_worker(rank, world, port, path, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cuvite_b200.dist import DistLouvain
+    from cuvite_b200 import vite_io
+    from fake_engine import OracleEngine
+    from oracle.binding import Oracle
+    loc, base, nv = vite_io.read_vite(path, rank, world)  # every rank reads its own rows of the Vite file
+    orc = Oracle()
+    orc.set_num_threads(1)
+    eng = OracleEngine(orc).upload(loc.offsets.numpy(), loc.tails.numpy(), loc.weights.numpy(), base=base, nv_global=nv)
+    _, _, _, comm = DistLouvain(eng, rank, world, nv).run(reference_numbering=True)
+    if rank == 0:
+        vite_io.write_communities(path + ".ours", comm)
+    ret[rank] = True
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_communities_file_equals_reference_cli(oracle, tmp_path):
+    """Vite file in -> <file>.communities out: the N-rank driver with reference_numbering writes
+    byte for byte what the reference's own CLI (oracle/_ref/gc_cpu64 -f file -o) writes."""
+    import subprocess
+    from cuvite_b200 import graphgen as gg, vite_io
+    exe = os.path.join(ROOT, "oracle", "_ref", "gc_cpu64")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gc_cpu64 not built (needs /root/reference at build time)")
+    f = str(tmp_path / "g.bin")
+    vite_io.write_vite(f, gg.rmat(10, seed=2))
+    r = subprocess.run([exe, "-f", f, "-o"], capture_output=True, text=True, timeout=600, cwd=str(tmp_path),
+                       env=dict(os.environ, OMP_NUM_THREADS="2"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_communities_worker, args=(2, 29933, f, ret), nprocs=2, join=True)
+    assert len(ret) == 2
+    assert open(f + ".ours").read() == open(f + ".communities").read()
+
+
 def test_partition_ranges_match_reference_formula():
     from cuvite_b200.vite_io import partition_ranges
     for nv, p in [(1024, 3), (7, 8), (1 << 20, 8), (30000, 7)]:
