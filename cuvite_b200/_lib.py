@@ -57,6 +57,7 @@ SIGNATURES = {
     "cvb_graph_from_pairs": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i64]),
     "cvb_graph_download": (_i32, [_vp, _vp, _vp, _vp]),
     "cvb_louvain_run": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp]),
+    "cvb_louvain_run_ex": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "cvb_launch_count": (_i64, [_vp]),
     "cvb_last_sweep_ms": (C.c_float, [_vp]),
 }

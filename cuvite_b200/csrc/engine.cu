@@ -1515,6 +1515,11 @@ int cvb_graph_download(cvb_engine *e, int64_t *offsets, int64_t *tails, double *
 
 int cvb_louvain_run(cvb_engine *e, int max_levels, double *level_q, int *level_iters, int64_t *level_nv,
                     int64_t *comm_out) {
+  return cvb_louvain_run_ex(e, max_levels, 0, level_q, level_iters, level_nv, comm_out);
+}
+
+int cvb_louvain_run_ex(cvb_engine *e, int max_levels, int flags, double *level_q, int *level_iters,
+                       int64_t *level_nv, int64_t *comm_out) {
   if (!e || !e->graph_ready) { set_error("cvb_louvain_run: no graph uploaded"); return CVB_ERR_STATE; }
   if (e->nvl != e->nvg) { set_error("cvb_louvain_run is the one-GPU driver"); return CVB_ERR_STATE; }
   cudaStream_t st = e->stream;
@@ -1528,10 +1533,14 @@ int cvb_louvain_run(cvb_engine *e, int max_levels, double *level_q, int *level_i
   }
   double curr = -1.0, prev = -1.0;  // main.cpp:177
   int phase = 0, tot_iters = 0;
-  const double threshold = 1.0e-6;  // main.cpp:239
+  double threshold = 1.0e-6;  // main.cpp:239
   while (true) {
     const int64_t nv = e->nvl;
     int iters = 0;
+    if (flags & CVB_RUN_THRESHOLD_CYCLING) {  // option -i, main.cpp:225-236 (short_phase == phase below the cap)
+      const int sp = phase % 13;
+      threshold = sp <= 2 ? 1.0e-3 : sp <= 6 ? 1.0e-4 : sp <= 9 ? 1.0e-5 : 1.0e-6;
+    }
     int rc = cvb_phase_run(e, curr, threshold, 0, &curr, &iters);  // main.cpp:344
     if (rc != CVB_OK) return rc;
     tot_iters += iters;

@@ -224,7 +224,15 @@ class DistLouvain:
         self._set_nv_global(nc)
         return newid, nc
 
-    def run(self, max_levels: int = 200, threshold: float = 1.0e-6, reference_numbering: bool = False):
+    @staticmethod
+    def cycled_threshold(short_phase: int) -> float:
+        """Threshold cycling (option -i), main.cpp:225-236: coarse thresholds first, 1e-6 last,
+        on a 13-phase cycle."""
+        sp = short_phase % 13
+        return 1.0e-3 if sp <= 2 else 1.0e-4 if sp <= 6 else 1.0e-5 if sp <= 9 else 1.0e-6
+
+    def run(self, max_levels: int = 200, threshold: float = 1.0e-6, reference_numbering: bool = False,
+            threshold_cycling: bool = False):
         """The default phase loop of main.cpp:218-495 across ranks.  Returns (level_q,
         level_iters (cumulative, as the reference prints them), level_nv, comm) where
         comm[i] is the final community of original GLOBAL vertex i (replicated tensor).
@@ -236,12 +244,19 @@ class DistLouvain:
         contiguous", main.cpp:375-396) before composing (main.cpp:397-404) — including the
         reference's quirk that this composition indexes level l's vertices (numbered by rebuild in
         first-appearance order) with level l-1's sorted-rank ids, so beyond the first level the
-        dumped ids describe the reference's output, not necessarily the partition found."""
+        dumped ids describe the reference's output, not necessarily the partition found.
+
+        ``threshold_cycling`` is the reference's -i (main.cpp:225-239, 482-483): the phase threshold —
+        both the sweep-loop exit and the level-acceptance test — follows ``cycled_threshold``.  (The
+        extra 1e-6 pass main.cpp:436-441 runs right before exiting changes no reported level and no
+        output file, so it is not run.)"""
         level_q, level_iters, level_nv = [], [], []
         comm, comm_ref, nv0 = None, None, self.nvg
         curr, prev, tot_iters, phase = -1.0, -1.0, 0, 0
         while True:
             nv = self.nvg
+            if threshold_cycling:
+                threshold = self.cycled_threshold(phase)  # short_phase == phase until the 200-phase cap
             curr, iters = self.run_phase(lower=curr, thresh=threshold)
             tot_iters += iters
             if (curr - prev) > threshold:  # main.cpp:361

@@ -159,13 +159,15 @@ class GpuGraph:
         check(self._L.cvb_coarsen(self._h, C.byref(n)), "coarsen")
         return n.value
 
-    def run(self, max_levels: int = 200):
+    def run(self, max_levels: int = 200, threshold_cycling: bool = False):
+        """cvb_louvain_run[_ex]: the phase loop of main.cpp:218-495 (threshold_cycling = option -i)."""
         nv0 = self.info().nv_local
         lq = np.zeros(max_levels)
         li = np.zeros(max_levels, np.int32)
         ln = np.zeros(max_levels, np.int64)
         comm = np.empty(nv0, np.int64)
-        n = self._L.cvb_louvain_run(self._h, max_levels, _ptr(lq), _ptr(li), _ptr(ln), _ptr(comm))
+        n = self._L.cvb_louvain_run_ex(self._h, max_levels, 1 if threshold_cycling else 0, _ptr(lq), _ptr(li),
+                                       _ptr(ln), _ptr(comm))
         if n < 0:
             check(n, "louvain_run")
         return list(lq[:n]), [int(x) for x in li[:n]], [int(x) for x in ln[:n]], comm

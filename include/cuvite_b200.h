@@ -257,6 +257,14 @@ int cvb_graph_download(cvb_engine *e, int64_t *offsets, int64_t *tails, double *
 int cvb_louvain_run(cvb_engine *e, int max_levels, double *level_q, int *level_iters,
                     int64_t *level_nv, int64_t *comm_out);
 
+/* Same with the reference's driver options.  CVB_RUN_THRESHOLD_CYCLING = option -i
+ * (main.cpp:225-239, 482-483): the phase threshold (sweep-loop exit and level acceptance)
+ * cycles 1e-3 x3, 1e-4 x4, 1e-5 x3, 1e-6 x3.  (The extra 1e-6 pass of main.cpp:436-441 right
+ * before exiting changes no reported level and no output, and is not run.) */
+enum { CVB_RUN_THRESHOLD_CYCLING = 1 };
+int cvb_louvain_run_ex(cvb_engine *e, int max_levels, int flags, double *level_q, int *level_iters,
+                       int64_t *level_nv, int64_t *comm_out);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Kernels launched by this engine since creation (bench.py "gpu_launches"). */
 int64_t cvb_launch_count(const cvb_engine *e);

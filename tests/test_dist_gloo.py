@@ -103,7 +103,7 @@ def test_distributed_multilevel_run_equals_one_rank_reference(oracle, world, nam
         assert ret[r][0], f"rank {r}: {ret[r]}"
 
 
-def _communities_worker(rank, world, port, path, ret):
+def _communities_worker(rank, world, port, path, ret, cycling=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -117,10 +117,10 @@ def _communities_worker(rank, world, port, path, ret):
     orc = Oracle()
     orc.set_num_threads(1)
     eng = OracleEngine(orc).upload(loc.offsets.numpy(), loc.tails.numpy(), loc.weights.numpy(), base=base, nv_global=nv)
-    _, _, _, comm = DistLouvain(eng, rank, world, nv).run(reference_numbering=True)
+    lq, li, _, comm = DistLouvain(eng, rank, world, nv).run(reference_numbering=True, threshold_cycling=cycling)
     if rank == 0:
         vite_io.write_communities(path + ".ours", comm)
-    ret[rank] = True
+    ret[rank] = (lq, li)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -143,6 +143,35 @@ def test_communities_file_equals_reference_cli(oracle, tmp_path):
     mp.spawn(_communities_worker, args=(2, 29933, f, ret), nprocs=2, join=True)
     assert len(ret) == 2
     assert open(f + ".ours").read() == open(f + ".communities").read()
+
+
+def test_threshold_cycling_equals_reference_cli(oracle, tmp_path):
+    """-i (threshold cycling, main.cpp:225-239): level lines (Q as printed, cumulative iterations) and
+    the community dump of the reference CLI, on a graph where -i changes the trajectory."""
+    import re
+    import subprocess
+    from cuvite_b200 import graphgen as gg, vite_io
+    exe = os.path.join(ROOT, "oracle", "_ref", "gc_cpu64")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gc_cpu64 not built (needs /root/reference at build time)")
+    f = str(tmp_path / "h.bin")
+    vite_io.write_vite(f, gg.erdos_renyi(3000, 8.0, seed=1))
+    outs = {}
+    for flag in ((), ("-i",)):
+        r = subprocess.run([exe, "-f", f, "-o", *flag], capture_output=True, text=True, timeout=600, cwd=str(tmp_path),
+                           env=dict(os.environ, OMP_NUM_THREADS="2"))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[flag] = (re.findall(r"Level \d+, Modularity: ([0-9.eE+-]+), Clustering time: [^,]*, Iterations: (\d+)", r.stdout),
+                      open(f + ".communities").read())
+    assert outs[()][0] != outs[("-i",)][0], "pick a graph where -i matters"
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_communities_worker, args=(2, 29944, f, ret, True), nprocs=2, join=True)
+    lq, li = ret[0]
+    want = outs[("-i",)]
+    assert [f"{q:.6g}" for q in lq] == [f"{float(q):.6g}" for q, _ in want[0]]
+    assert li == [int(i) for _, i in want[0]]
+    assert open(f + ".ours").read() == want[1]
 
 
 def test_partition_ranges_match_reference_formula():

@@ -363,3 +363,31 @@ def test_staged_coarsening_driver_matches_golden(name):
     assert lq == list(g["level_q"]) and li == list(g["level_iters"]) and ln == list(g["level_nv"])
     assert np.array_equal(comm.cpu().numpy(), g["comm"])
     gpu.close()
+
+
+def test_threshold_cycling_matches_reference_cli(tmp_path):
+    """cvb_louvain_run_ex(CVB_RUN_THRESHOLD_CYCLING) == the reference CLI with -i (main.cpp:225-239) on
+    a graph where -i changes the trajectory: Q as printed (6 significant digits) and cumulative
+    iterations per level."""
+    import os
+    import re
+    import subprocess
+    from cuvite_b200 import graphgen as gg, vite_io
+    from cuvite_b200.engine import GpuGraph
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "gc_cpu64")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gc_cpu64 not built (needs /root/reference at build time)")
+    g = gg.erdos_renyi(3000, 8.0, seed=1)
+    f = str(tmp_path / "h.bin")
+    vite_io.write_vite(f, g)
+    r = subprocess.run([exe, "-f", f, "-i"], capture_output=True, text=True, timeout=600, cwd=str(tmp_path),
+                       env=dict(os.environ, OMP_NUM_THREADS="4"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    want = re.findall(r"Level \d+, Modularity: ([0-9.eE+-]+), Clustering time: [^,]*, Iterations: (\d+)", r.stdout)
+    assert want
+    gpu = GpuGraph()
+    gpu.upload(g.offsets.numpy(), g.tails.numpy(), g.weights.numpy())
+    lq, li, _, _ = gpu.run(threshold_cycling=True)
+    gpu.close()
+    assert [f"{q:.6g}" for q in lq] == [f"{float(q):.6g}" for q, _ in want]
+    assert li == [int(i) for _, i in want]
