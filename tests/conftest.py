@@ -42,7 +42,7 @@ def load_golden(name):
     return np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz"))
 
 
-GOLDEN = ["ring6x5", "er1k", "rmat10", "rmat10_intw", "rmat9_realw", "hub30k", "empty_rows"]
+GOLDEN = ["ring6x5", "er1k", "rmat10", "rmat10_intw", "rmat9_realw", "hub30k", "empty_rows", "multi9"]
 
 
 @pytest.fixture(scope="session")

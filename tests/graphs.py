@@ -42,6 +42,28 @@ def hub_graph(nv=30000, seed=7):
     return _np(gg.csr_from_pairs(nv, s, d))
 
 
+def multigraph(scale=9, seed=6):
+    """A NON-simple Vite-style input: parallel entries (both directions duplicated), self-loops (some
+    stored twice), integer weights 1..3 and rows in shuffled (not ascending) order."""
+    o, t, _ = _np(gg.rmat(scale, seed=seed))
+    nv = o.size - 1
+    src = np.repeat(np.arange(nv, dtype=np.int64), np.diff(o))
+    h = _sym_hash(o, t)
+    w = (1 + h % 3).astype(np.float64)
+    dup = (h % 5) == 0  # symmetric predicate: (i,j) and (j,i) are duplicated together
+    loops = np.arange(0, nv, 7, dtype=np.int64)
+    loops2 = np.arange(0, nv, 21, dtype=np.int64)
+    s = np.concatenate([src, src[dup], loops, loops2])
+    d = np.concatenate([t, t[dup], loops, loops2])
+    ww = np.concatenate([w, w[dup], np.full(loops.size, 2.0), np.full(loops2.size, 1.0)])
+    rng = np.random.default_rng(seed)
+    order = np.lexsort((rng.random(s.size), s))  # rows contiguous, entries of a row shuffled
+    s, d, ww = s[order], d[order], ww[order]
+    off = np.zeros(nv + 1, np.int64)
+    np.cumsum(np.bincount(s, minlength=nv), out=off[1:])
+    return off, d, ww
+
+
 def small_cases():
     """name -> (offsets, tails, weights); all small enough for committed fixtures."""
     cases = {
@@ -52,5 +74,6 @@ def small_cases():
         "rmat9_realw": with_real_weights(*_np(gg.rmat(9, seed=5))),
         "hub30k": hub_graph(),
         "empty_rows": _np(gg.csr_from_pairs(64, torch.tensor([1, 5, 9, 9]), torch.tensor([2, 6, 10, 11]))),
+        "multi9": multigraph(),
     }
     return cases

@@ -89,7 +89,7 @@ def _run_worker(rank, world, port, name, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,name", [(2, "rmat10_intw"), (3, "er1k"), (2, "ring6x5"), (3, "hub30k")])
+@pytest.mark.parametrize("world,name", [(2, "rmat10_intw"), (3, "er1k"), (2, "ring6x5"), (3, "hub30k"), (2, "multi9")])
 def test_distributed_multilevel_run_equals_one_rank_reference(oracle, world, name):
     """Phases + distributed coarsening (all-gathered cvect, 1-rank numbering, all-to-all of the
     contracted pairs, owner-side merge) reproduce the one-rank reference's levels and final
