@@ -4,6 +4,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <mutex>
+#include <set>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -207,14 +210,21 @@ struct cvb_engine {
 
 namespace {
 
+// cudaFuncSetAttribute is per device: remember (device, kernel) pairs, not one flag per kernel,
+// so that engines on several devices of one process all get their dynamic shared memory opt-in
+bool first_use_on_device(int device, const void *kernel) {
+  static std::mutex m;
+  static std::set<std::pair<int, const void *>> seen;
+  std::lock_guard<std::mutex> lock(m);
+  return seen.insert({device, kernel}).second;
+}
+
 template <typename W, int CAP>
 int launch_warp(cvb_engine *e, const SweepParams &p, const vid_t *list, int64_t n) {
   const size_t smem = (sizeof(W) + sizeof(vid_t)) * CAP * 4;
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device(e->device, reinterpret_cast<const void *>(&k_sweep_warp<W, CAP>))) {
     CVB_CUDA(cudaFuncSetAttribute(k_sweep_warp<W, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-    configured = true;
   }
   const int grid = static_cast<int>((n + 3) / 4);
   k_sweep_warp<W, CAP><<<grid, 128, smem, e->stream>>>(p, list, static_cast<int>(n));
@@ -225,11 +235,9 @@ int launch_warp(cvb_engine *e, const SweepParams &p, const vid_t *list, int64_t 
 template <typename W, int CAP, int THREADS>
 int launch_block(cvb_engine *e, const SweepParams &p, const vid_t *list, int64_t n) {
   const size_t smem = (sizeof(W) + sizeof(vid_t)) * CAP;
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device(e->device, reinterpret_cast<const void *>(&k_sweep_block<W, CAP, THREADS, false>))) {
     CVB_CUDA(cudaFuncSetAttribute(k_sweep_block<W, CAP, THREADS, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
   }
   k_sweep_block<W, CAP, THREADS, false>
       <<<static_cast<int>(n), THREADS, smem, e->stream>>>(p, list, static_cast<int>(n), nullptr, 0, 0);
@@ -293,11 +301,9 @@ int launch_hash_impl(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, co
   constexpr int VPB = TPV <= 32 ? 256 / TPV : 1;
   constexpr int THREADS = TPV <= 32 ? 256 : TPV;
   const size_t smem = hash_block_smem<TPV, KC, NCH, TMA>();
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device(e->device, reinterpret_cast<const void *>(&k_sweep_u32_hash<TPV, KC, NCH, MINB, TMA>))) {
     CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_hash<TPV, KC, NCH, MINB, TMA>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
   }
   int64_t grid = (n + VPB - 1) / VPB;
   const int64_t cap = static_cast<int64_t>(e->num_sms) * MINB;
@@ -316,11 +322,9 @@ int launch_hash(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const v
 template <int CS>
 int launch_cluster(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const vid_t *list, int64_t n) {
   const size_t smem = static_cast<size_t>(kClusterSlice) * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device(e->device, reinterpret_cast<const void *>(&k_sweep_u32_cluster<CS>))) {
     CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_cluster<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-    configured = true;
   }
   int64_t nclusters = n;
   const int64_t cap = e->num_sms / CS;
@@ -419,10 +423,8 @@ int launch_sweep_u32(cvb_engine *e) {
   const int gcls = e->global_table_class();
   if (!e->use_cluster && e->use_twopass && (n = cnt(kClsC2)) > 0) {
     constexpr int kTwoPassSmem = 16384 * 8;
-    static bool twopass_configured = false;
-    if (!twopass_configured) {
+    if (first_use_on_device(e->device, reinterpret_cast<const void *>(&k_sweep_u32_twopass))) {
       CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_twopass, cudaFuncAttributeMaxDynamicSharedMemorySize, kTwoPassSmem));
-      twopass_configured = true;
     }
     const int grid = static_cast<int>(n < e->num_sms ? n : e->num_sms);
     k_sweep_u32_twopass<<<grid, 1024, kTwoPassSmem, e->aux[1]>>>(p, lst(kClsC2), static_cast<int>(n));
@@ -443,19 +445,15 @@ int launch_sweep_u32(cvb_engine *e) {
     gt.piece_gain = e->gpiece_gain.p;
     gt.piece_key = e->gpiece_key.p;
     constexpr int kGiantSmem = 2 * kGiantChunk * 8;
-    static bool giant_configured = false;
-    if (!giant_configured) {
+    if (first_use_on_device(e->device, reinterpret_cast<const void *>(&k_sweep_u32_giant_insert<false>))) {
       CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_giant_insert<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGiantSmem));
-      giant_configured = true;
     }
     gt.dense = e->dense.p;
     gt.dense_stride = e->dense_stride;
     gt.kcount = e->kcount.p;
     gt.klist = e->klist.p;
-    static bool giant_configured2 = false;
-    if (!giant_configured2) {
+    if (first_use_on_device(e->device, reinterpret_cast<const void *>(&k_sweep_u32_giant_insert<true>))) {
       CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_giant_insert<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGiantSmem));
-      giant_configured2 = true;
     }
     for (const auto &b : e->giant_batches) {
       gt.slot_base = b.slot_base;
