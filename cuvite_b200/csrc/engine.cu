@@ -187,6 +187,7 @@ struct cvb_engine {
   bool use_tma = false;        // CVB_TMA=1: cp.async.bulk + mbarrier staging of tails/weights tiles
   bool use_cluster = false;    // CVB_CLUSTER=1: DSMEM cluster kernels for 8193..65536
   bool use_twopass = true;     // 8193..16384: two-pass shared-memory kernel (CVB_NO_TWOPASS=1: global tables)
+  bool l2_persist = false;     // CVB_L2_PERSIST=1: access-policy window that keeps `packed` persisting in L2 (unmeasured A/B)
   // first degree class that goes through the global tables
   int global_table_class() const { return use_cluster ? kClsGiant : (use_twopass ? kClsC4 : kClsC2); }
   bool giant_direct = false;   // CVB_GIANT_DIRECT=1: giant entries go straight to the global tables
@@ -600,6 +601,29 @@ int post_graph(cvb_engine *e) {
   }
   if (e->mode == CVB_WEIGHTS_U32) {
     CVB_TRY(e->packed.ensure(e->nvg + 1));
+    if (e->l2_persist && e->nvg > 0) {
+      // the label gather only runs at L2 speed if the gathered array lives there; for graphs
+      // whose `packed` array approaches the L2 size, pin (part of) it with an access-policy window on every
+      // stream the sweep kernels run on; everything else (the CSR stream) is marked streaming on a miss
+      cudaDeviceProp prop;
+      CVB_CUDA(cudaGetDeviceProperties(&prop, e->device));
+      const size_t bytes = static_cast<size_t>(e->nvg) * sizeof(uint2);
+      size_t carve = bytes < static_cast<size_t>(prop.persistingL2CacheMaxSize) ? bytes : prop.persistingL2CacheMaxSize;
+      if (carve > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        CVB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = e->packed.p;
+        attr.accessPolicyWindow.num_bytes =
+            bytes < static_cast<size_t>(prop.accessPolicyMaxWindowSize) ? bytes : prop.accessPolicyMaxWindowSize;
+        const double ratio = static_cast<double>(carve) / static_cast<double>(attr.accessPolicyWindow.num_bytes);
+        attr.accessPolicyWindow.hitRatio = static_cast<float>(ratio > 1.0 ? 1.0 : ratio);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CVB_CUDA(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+        for (int i = 0; i < cvb_engine::kAux; ++i)
+          CVB_CUDA(cudaStreamSetAttribute(e->aux[i], cudaStreamAttributeAccessPolicyWindow, &attr));
+      }
+    }
     CVB_TRY(e->d_flags.ensure(4));
     CVB_CUDA(cudaMemsetAsync(e->d_flags.p, 0, 4 * sizeof(int), st));
     if (e->nvl > 0) {
@@ -788,6 +812,7 @@ cvb_engine *cvb_create(void *stream) {
   }
   if (const char *s = getenv("CVB_CLUSTER")) e->use_cluster = (s[0] == '1');
   if (const char *s = getenv("CVB_NO_TWOPASS")) e->use_twopass = (s[0] != '1');
+  if (const char *s = getenv("CVB_L2_PERSIST")) e->l2_persist = (s[0] == '1');
   if (const char *s = getenv("CVB_BIG_DENSE")) e->big_dense = (s[0] != '0');
   if (const char *s = getenv("CVB_BIG_DENSE_MB")) {
     const long mb = atol(s);
