@@ -187,6 +187,8 @@ struct cvb_engine {
   bool use_tma = false;        // CVB_TMA=1: cp.async.bulk + mbarrier staging of tails/weights tiles
   bool use_cluster = false;    // CVB_CLUSTER=1: DSMEM cluster kernels for 8193..65536
   bool use_twopass = true;     // 8193..16384: two-pass shared-memory kernel (CVB_NO_TWOPASS=1: global tables)
+  bool use_split = false;      // CVB_SPLIT=1: hash classes gather 4-byte labels, degrees per distinct community (unmeasured A/B)
+  DevBuf<uint32_t> cdeg32;
   bool l2_persist = false;     // CVB_L2_PERSIST=1: access-policy window that keeps `packed` persisting in L2 (unmeasured A/B)
   // first degree class that goes through the global tables
   int global_table_class() const { return use_cluster ? kClsGiant : (use_twopass ? kClsC4 : kClsC2); }
@@ -297,25 +299,27 @@ int launch_sweep(cvb_engine *e) {
   return CVB_OK;
 }
 
-template <int TPV, int KC, int NCH, int MINB, bool TMA>
+template <int TPV, int KC, int NCH, int MINB, bool TMA, bool SPLIT = false>
 int launch_hash_impl(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const vid_t *list, int64_t n) {
   constexpr int VPB = TPV <= 32 ? 256 / TPV : 1;
   constexpr int THREADS = TPV <= 32 ? 256 : TPV;
   const size_t smem = hash_block_smem<TPV, KC, NCH, TMA>();
-  if (first_use_on_device(e->device, reinterpret_cast<const void *>(&k_sweep_u32_hash<TPV, KC, NCH, MINB, TMA>))) {
-    CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_hash<TPV, KC, NCH, MINB, TMA>,
+  if (first_use_on_device(e->device, reinterpret_cast<const void *>(&k_sweep_u32_hash<TPV, KC, NCH, MINB, TMA, SPLIT>))) {
+    CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_hash<TPV, KC, NCH, MINB, TMA, SPLIT>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
   int64_t grid = (n + VPB - 1) / VPB;
   const int64_t cap = static_cast<int64_t>(e->num_sms) * MINB;
   if (grid > cap) grid = cap;
-  k_sweep_u32_hash<TPV, KC, NCH, MINB, TMA><<<static_cast<int>(grid), THREADS, smem, st>>>(p, list, static_cast<int>(n));
+  k_sweep_u32_hash<TPV, KC, NCH, MINB, TMA, SPLIT>
+      <<<static_cast<int>(grid), THREADS, smem, st>>>(p, list, static_cast<int>(n));
   e->launches++;
   return CVB_OK;
 }
 
 template <int TPV, int KC, int NCH, int MINB>
 int launch_hash(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const vid_t *list, int64_t n) {
+  if (e->use_split) return launch_hash_impl<TPV, KC, NCH, MINB, false, true>(e, st, p, list, n);
   if (TPV >= 128 && e->use_tma) return launch_hash_impl<TPV, KC, NCH, MINB, (TPV >= 128)>(e, st, p, list, n);
   return launch_hash_impl<TPV, KC, NCH, MINB, false>(e, st, p, list, n);
 }
@@ -367,6 +371,15 @@ int launch_sweep_u32(cvb_engine *e) {
   p.cw = e->cw.p;
   p.ddeg = e->labels_only ? nullptr : e->ddeg.p;  // labels-only exchange derives the deltas from labels
   p.dsize = e->labels_only ? nullptr : e->dsize.p;
+  p.labels = e->sweep_labels();
+  p.csize = e->csize.p;
+  p.cdeg32 = nullptr;
+  if (e->use_split) {
+    CVB_TRY(e->cdeg32.ensure(e->nvg + 1));
+    k_cdeg32<<<grid_for(e->nvg, 256), 256, 0, st>>>(e->nvg, e->cdeg.p, e->cdeg32.p);
+    e->launches++;
+    p.cdeg32 = e->cdeg32.p;
+  }
   auto cnt = [&](int c) { return e->class_start[c + 1] - e->class_start[c]; };
   auto lst = [&](int c) { return e->list.p + e->class_start[c]; };
   int64_t n;
@@ -813,6 +826,7 @@ cvb_engine *cvb_create(void *stream) {
   if (const char *s = getenv("CVB_CLUSTER")) e->use_cluster = (s[0] == '1');
   if (const char *s = getenv("CVB_NO_TWOPASS")) e->use_twopass = (s[0] != '1');
   if (const char *s = getenv("CVB_L2_PERSIST")) e->l2_persist = (s[0] == '1');
+  if (const char *s = getenv("CVB_SPLIT")) e->use_split = (s[0] == '1');
   if (const char *s = getenv("CVB_BIG_DENSE")) e->big_dense = (s[0] != '0');
   if (const char *s = getenv("CVB_BIG_DENSE_MB")) {
     const long mb = atol(s);
@@ -860,6 +874,7 @@ void cvb_destroy(cvb_engine *e) {
   e->partials.release(); e->d_sums.release(); e->ticket.release(); e->d_flags.release();
   e->h_sums.release(); e->staging.release(); e->staging2.release(); e->giant.release(); e->h_stage.release();
   e->packed.release(); e->giant_layout.release(); e->gslots.release(); e->pair_keys.release(); e->pair_w.release();
+  e->cdeg32.release();
   e->dense.release(); e->kcount.release(); e->klist.release(); e->gchunk2_gain.release(); e->gchunk2_key.release();
   e->gmeta.release(); e->gpiece_key.release(); e->gpiece_gain.release(); e->gchunk_gain.release();
   e->gchunk_key.release(); e->gchunk_owner.release(); e->big_layout.release(); e->big_owner.release();

@@ -42,7 +42,17 @@ struct SweepU32Params {
   double *__restrict__ cw;     // [nv_local]
   double *__restrict__ ddeg;   // [nv_global]
   int32_t *__restrict__ dsize; // [nv_global]
+  // split-gather variant (CVB_SPLIT=1): 4-byte label gather per entry, community degree per DISTINCT community
+  const vid_t *__restrict__ labels;      // [nv_global] the labels every sweep reads
+  const uint32_t *__restrict__ cdeg32;   // [nv_global] (uint32) cdeg
+  const int32_t *__restrict__ csize;     // [nv_global]
 };
+
+__global__ void k_cdeg32(int64_t nv_global, const double *__restrict__ cdeg, uint32_t *__restrict__ cdeg32) {
+  for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < nv_global;
+       c += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    cdeg32[c] = static_cast<uint32_t>(cdeg[c]);
+}
 
 // packed[v] = {labels[v] | (csize[labels[v]] == 1) << 31, (uint32) cdeg[labels[v]]}
 __global__ void k_pack_labels(int64_t nv_global, const vid_t *__restrict__ labels, const double *__restrict__ cdeg,
@@ -388,6 +398,16 @@ __device__ __forceinline__ uint32_t table_insert_chunk(uint32_t kaddr, uint32_t 
   return fresh;
 }
 
+// split-gather variant: keys carry no singleton flag; the committing lane reads the winner's community size
+// (only needed when the vertex itself is a singleton: louvain.cpp:2240-2241)
+template <bool SPLIT>
+__device__ __forceinline__ uint32_t winner_with_singleton_bit(const SweepU32Params &p, uint32_t me_key, uint32_t wid,
+                                                              double wg) {
+  if (SPLIT && wg > 0.0 && (me_key & kSingletonBit) && wid != kLabelMask && p.csize[wid & kLabelMask] == 1)
+    wid |= kSingletonBit;
+  return wid;
+}
+
 struct VertexHeader {
   vid_t v;
   eid_t e0, e1;
@@ -416,7 +436,12 @@ __device__ __forceinline__ VertexHeader fetch_header(const SweepU32Params &p, vi
 // B200 (scale-20) this single-stage staging is ~10 % SLOWER than per-thread streaming loads
 // (the copy is issued only after the previous tile is consumed, and the tile costs occupancy),
 // so it is off by default; see DESIGN.md.
-template <int TPV, int KC, int NCH, int MINB, bool TMA = false>
+// SPLIT = true (CVB_SPLIT=1, A/B variant added at the end of round 1, not measured yet): the per-entry gather
+// reads the 4-byte label array instead of the 8-byte `packed` record — half the L2 footprint, which is what
+// decides the hit rate once nv_global * 8 B approaches the L2 size (scale 24; 8-GPU weak scaling) — and the
+// community degree is gathered once per DISTINCT neighbour community at evaluation time (no cay[] registers
+// during the insert phase); the singleton flag of the winner is read at commit time.
+template <int TPV, int KC, int NCH, int MINB, bool TMA = false, bool SPLIT = false>
 __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
     k_sweep_u32_hash(SweepU32Params p, const vid_t *__restrict__ list, int n) {
   extern __shared__ __align__(16) uint32_t smem_u32[];
@@ -531,10 +556,15 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
         uint32_t active = 0u;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
-          const uint2 pk = p.packed[tail[k]];
           const bool valid = (validm >> k) & 1u;
-          key[k] = valid ? pk.x : kEmptyKeyU;
-          cay[c * KC + k] = pk.y;
+          if (SPLIT) {
+            const uint32_t lb = static_cast<uint32_t>(p.labels[tail[k]]);
+            key[k] = valid ? lb : kEmptyKeyU;
+          } else {
+            const uint2 pk = p.packed[tail[k]];
+            key[k] = valid ? pk.x : kEmptyKeyU;
+            cay[c * KC + k] = pk.y;
+          }
           const bool own = (key[k] & kLabelMask) == cc;  // idle lanes: 0x7fffffff is never a label
           ownsum += own ? w[k] : 0u;
           selfsum += (valid && tail[k] == self) ? w[k] : 0u;
@@ -576,6 +606,10 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
     const double ax = static_cast<double>(me.y) - vd;
     double g = -1.0;
     uint32_t id = kLabelMask;
+    if (SPLIT) {  // community degrees of this lane's claims: all gathers in flight before the first use
+#pragma unroll
+      for (int q = 0; q < K; ++q) cay[q] = (freshmask & (1u << q)) ? p.cdeg32[ckey[q] & kLabelMask] : 0u;
+    }
 #pragma unroll
     for (int q = 0; q < K; ++q)
       if (freshmask & (1u << q)) {
@@ -593,7 +627,7 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
     uint32_t wid = id;
     if (TPV > 1) wid = group_argmax<GL>(g, id, &wg, gmask);
     if (TPV <= 32) {
-      if (tid == 0) commit_vertex_u32(p, v, me.x, wg, wid, vd, counter0);
+      if (tid == 0) commit_vertex_u32(p, v, me.x, wg, winner_with_singleton_bit<SPLIT>(p, me.x, wid, wg), vd, counter0);
       __syncwarp(gmask);
     } else {
       if (lane == 0) {
@@ -607,7 +641,7 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
             wg = red_g[i];
             wid = red_id[i];
           }
-        commit_vertex_u32(p, v, me.x, wg, wid, vd, counter0);
+        commit_vertex_u32(p, v, me.x, wg, winner_with_singleton_bit<SPLIT>(p, me.x, wid, wg), vd, counter0);
         meta[1] = 0u;
         meta[2] = 0u;
       }
