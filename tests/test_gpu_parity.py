@@ -430,6 +430,23 @@ def test_non_simple_input_matches_reference():
     gpu.close()
 
 
+def test_config_c1_er16k_full_run_matches_oracle(oracle):
+    """BASELINE config 1 (16K-vertex Erdos-Renyi, p = 16/n): full multi-phase run on the GPU equals the
+    oracle level by level and vertex by vertex (the oracle equals the reference CLI on this graph:
+    tests/test_oracle_pin.py::test_config_c1_er16k_reference_cli_vs_oracle)."""
+    from cuvite_b200 import graphgen as gg
+    from cuvite_b200.engine import GpuGraph
+    g = gg.erdos_renyi(16384, 16.0, seed=1)
+    o, t, w = g.offsets.numpy(), g.tails.numpy(), g.weights.numpy()
+    want = oracle.run(o, t, w)
+    gpu = GpuGraph()
+    gpu.upload(o, t, w)
+    lq, li, ln, comm = gpu.run()
+    gpu.close()
+    assert lq == want.level_q and li == want.level_iters and ln == want.level_nv
+    assert np.array_equal(comm, want.comm)
+
+
 @pytest.mark.xfail(strict=False, reason="CVB_SPLIT=1 / CVB_L2_PERSIST=1 are A/B variants written after the last GPU "
                                         "run of round 1 (no GPU minutes left): first executed by this test")
 @pytest.mark.parametrize("name", ["rmat10_intw", "hub30k"])
