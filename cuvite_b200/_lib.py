@@ -15,6 +15,11 @@ LIB_PATH = os.path.join(_HERE, "libcuvite_b200.so")
 _vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int, C.c_double
 
 
+class VitePart(C.Structure):
+    _fields_ = [("nv_global", _i64), ("ne_global", _i64), ("base", _i64), ("nv_local", _i64),
+                ("first_entry", _i64), ("ne_local", _i64)]
+
+
 class GraphInfo(C.Structure):
     _fields_ = [("nv_local", _i64), ("base", _i64), ("nv_global", _i64), ("ne_local", _i64),
                 ("weight_mode", C.c_int32), ("num_classes", C.c_int32),
@@ -56,6 +61,9 @@ SIGNATURES = {
     "cvb_contract_local": (_i32, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "cvb_graph_from_pairs": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i64]),
     "cvb_graph_download": (_i32, [_vp, _vp, _vp, _vp]),
+    "cvb_vite_partition": (_i32, [C.c_char_p, _i32, _i32, _i32, C.POINTER(VitePart), _vp]),
+    "cvb_vite_read_rows": (_i32, [C.c_char_p, C.POINTER(VitePart), _vp, _vp]),
+    "cvb_graph_load_vite": (_i32, [_vp, C.c_char_p, _i32, _i32, _i32, C.POINTER(VitePart)]),
     "cvb_louvain_run": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "cvb_louvain_run_ex": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "cvb_launch_count": (_i64, [_vp]),

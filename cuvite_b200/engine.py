@@ -100,6 +100,15 @@ class GpuGraph:
               "upload_aos")
         return self
 
+    def load_vite(self, path: str, rank: int = 0, nparts: int = 1, balanced: bool = False):
+        """cvb_graph_load_vite: this rank's rows of a Vite file -> pinned staging -> device.  Returns the
+        partition record (nv_global, ne_global, base, nv_local, first_entry, ne_local)."""
+        from ._lib import VitePart
+        part = VitePart()
+        check(self._L.cvb_graph_load_vite(self._h, path.encode(), rank, nparts, 1 if balanced else 0, C.byref(part)),
+              "graph_load_vite")
+        return part
+
     def upload_device(self, offsets, tails, weights, base: int = 0, nv_global: int | None = None):
         """Device-resident CSR (torch CUDA tensors: int64, int64, float64)."""
         import torch
@@ -263,6 +272,25 @@ class GpuGraph:
     @property
     def handle(self):
         return self._h
+
+
+def vite_partition(path: str, rank: int, nparts: int, balanced: bool = False):
+    """cvb_vite_partition (pure host code of the C ABI): (partition record, all range starts)."""
+    from ._lib import VitePart, load
+    part, parts = VitePart(), np.zeros(nparts + 1, np.int64)
+    check(load().cvb_vite_partition(path.encode(), rank, nparts, 1 if balanced else 0, C.byref(part), _ptr(parts)),
+          "vite_partition")
+    return part, parts
+
+
+def vite_read_rows(path: str, part):
+    """cvb_vite_read_rows (pure host code): (offsets rebased to 0, AoS edges) of the partition."""
+    from ._lib import load
+    off = np.empty(part.nv_local + 1, np.int64)
+    edges = np.empty(part.ne_local, dtype=[("tail", "<i8"), ("weight", "<f8")])
+    check(load().cvb_vite_read_rows(path.encode(), C.byref(part), _ptr(off), _ptr(edges) if part.ne_local else None),
+          "vite_read_rows")
+    return off, edges
 
 
 def gpu_for_louvain_iteration(nv, offsets, edges_aos, currComm, targetComm, vDegree, localCinfo_size,

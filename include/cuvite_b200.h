@@ -245,6 +245,28 @@ int cvb_contract_local(cvb_engine *e, const int32_t *d_newid_global, int64_t n_c
 int cvb_graph_from_pairs(cvb_engine *e, int64_t nv_local, int64_t base, int64_t nv_global,
                          const uint64_t *d_keys, const void *d_weights, int64_t n_pairs);
 
+/* ---- Vite binary files (distgraph.cpp) --------------------------------------- */
+
+/* Which rows of a Vite file rank `rank` of `nparts` owns: the reference's vertex ranges
+ * parts[p] = nv*p / P (loadDistGraphMPIIO, distgraph.cpp:69-203, :118-119) or, with
+ * `balanced`, its -b edge-balanced ranges (balanceEdges, distgraph.cpp:22-66 — restated
+ * loop for loop, incl. its off-by-one charging).  parts_out (nparts+1, may be NULL) gets
+ * all range starts.  Pure host code. */
+typedef struct cvb_vite_part {
+  int64_t nv_global, ne_global; /* file header                                   */
+  int64_t base, nv_local;       /* this rank's rows [base, base + nv_local)       */
+  int64_t first_entry, ne_local;/* its slice of the edge list                     */
+} cvb_vite_part;
+int cvb_vite_partition(const char *path, int rank, int nparts, int balanced, cvb_vite_part *out,
+                       int64_t *parts_out);
+/* Read those rows: offsets[nv_local+1] rebased to 0 (distgraph.cpp:194-195) and the AoS
+ * Edge{int64 tail; double weight} slice (HOST buffers of the caller).  Pure host code. */
+int cvb_vite_read_rows(const char *path, const cvb_vite_part *part, int64_t *offsets, void *edges_aos);
+/* File -> engine: partition, read into pinned staging, cvb_graph_upload_host.  Replaces
+ * loadDistGraphMPIIO[Balanced] + the first gpu_for_louvain_iteration upload. */
+int cvb_graph_load_vite(cvb_engine *e, const char *path, int rank, int nparts, int balanced,
+                        cvb_vite_part *out);
+
 /* D2H of the engine's current graph in the boundary layout (for writing Vite
  * files / handing the next level back to the reference's DistGraph). */
 int cvb_graph_download(cvb_engine *e, int64_t *offsets, int64_t *tails, double *weights);

@@ -447,6 +447,31 @@ def test_config_c1_er16k_full_run_matches_oracle(oracle):
     assert np.array_equal(comm, want.comm)
 
 
+def test_native_vite_load_matches_upload(tmp_path):
+    """cvb_graph_load_vite (file -> pinned staging -> device, reference: loadDistGraphMPIIO + first plugin upload):
+    same phase result as uploading the arrays; a partitioned load reports the reference's ranges."""
+    from cuvite_b200 import vite_io
+    from cuvite_b200.engine import GpuGraph
+    from cuvite_b200.graphgen import CSRGraph
+    import torch
+    g = load_golden("rmat10_intw")
+    o, t, w = _csr(g)
+    f = str(tmp_path / "g.bin")
+    vite_io.write_vite(f, CSRGraph(o.size - 1, torch.from_numpy(o), torch.from_numpy(t), torch.from_numpy(w)))
+    gpu = GpuGraph()
+    part = gpu.load_vite(f)
+    assert (part.nv_global, part.base, part.nv_local, part.ne_local) == (o.size - 1, 0, o.size - 1, t.size)
+    q, iters = gpu.phase_run()
+    assert (q, iters) == (float(g["q"]), int(g["iters"])) and np.array_equal(gpu.labels(0), g["cvect"])
+    part = gpu.load_vite(f, rank=1, nparts=3, balanced=True)
+    parts = vite_io.balanced_ranges(o, 3)
+    info = gpu.info()
+    assert (part.base, part.nv_local) == (parts[1], parts[2] - parts[1])
+    assert (info.base, info.nv_local, info.nv_global, info.ne_local) == (parts[1], parts[2] - parts[1], o.size - 1,
+                                                                        int(o[parts[2]] - o[parts[1]]))
+    gpu.close()
+
+
 @pytest.mark.xfail(strict=False, reason="CVB_SPLIT=1 / CVB_L2_PERSIST=1 are A/B variants written after the last GPU "
                                         "run of round 1 (no GPU minutes left): first executed by this test")
 @pytest.mark.parametrize("name", ["rmat10_intw", "hub30k"])
