@@ -45,6 +45,16 @@ using eid_t = int64_t;
 
 constexpr vid_t kEmptyKey = -1;
 
+#ifdef __CUDACC__
+// Exact uint32 -> double without the conversion unit: 2^52 + x is representable with x in the low
+// mantissa word, and subtracting 2^52 is exact.  Measured on B200 (profiles/r02_lm_v2_raw.csv):
+// I2F.F64.U32 runs on the XU pipe, which the two conversions per CSR entry of the sweep kept 57 %
+// busy — as limiting as the L1TEX pipe; this form is one DADD on the (idle) FP64 pipe.
+__device__ __forceinline__ double u32_to_f64(uint32_t x) {
+  return __hiloint2double(0x43300000, static_cast<int>(x)) - 4503599627370496.0;
+}
+#endif
+
 // Degree classes.  Boundaries are inclusive upper degrees.
 enum : int {
   kClsZero = 0,  // deg == 0: never moves, no work

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <map>
 #include <mutex>
 #include <set>
 #include <utility>
@@ -13,6 +14,7 @@
 #include "setup.cuh"
 #include "sweep.cuh"
 #include "sweep_u32.cuh"
+#include "lm.cuh"
 #include "coarsen.cuh"
 
 namespace cvb {
@@ -189,9 +191,27 @@ struct cvb_engine {
   bool use_twopass = true;     // 8193..16384: two-pass shared-memory kernel (CVB_NO_TWOPASS=1: global tables)
   bool use_split = false;      // CVB_SPLIT=1: hash classes gather 4-byte labels, degrees per distinct community (unmeasured A/B)
   DevBuf<uint32_t> cdeg32;
+  // second-generation kernels (lm.cuh): per-vertex records in class-list order, self-loop weights
+  DevBuf<VertexRec> vrec;
+  DevBuf<uint32_t> selfw;
+  DevBuf<uint2> mp_stage;      // multi-pass kernel: staged packed records of the 8193..65536 rows
+  DevBuf<uint32_t> mp_off, mp_deg;
+  DevBuf<int> mp_redo;
+  bool use_mp = true;          // CVB_MP=0: two-pass + global-table kernels for those rows
+  bool mp_ready = false;
+  DevBuf<vid_t> rank, tails_r;  // degree-ordered gather layout (one GPU): rank[v], tails mapped to ranks
+  bool remap = false;          // the sweep reads tails_r / rank-ordered packed[]
+  bool use_remap = true;       // CVB_REMAP=0 disables it
+  bool use_lm = true;          // CVB_LM=0: first-generation hash/group kernels
+  bool lm_ready = false;       // vrec/selfw built for the current graph (U32 mode, < 2^32 entries)
+  bool unit_weights = false;   // every weight == 1: the sweep never reads the weights array
+  bool has_selfloops = false;
   bool l2_persist = false;     // CVB_L2_PERSIST=1: access-policy window that keeps `packed` persisting in L2 (unmeasured A/B)
   // first degree class that goes through the global tables
-  int global_table_class() const { return use_cluster ? kClsGiant : (use_twopass ? kClsC4 : kClsC2); }
+  int global_table_class() const {
+    if (use_lm && lm_ready && use_mp) return kClsGiant;
+    return use_cluster ? kClsGiant : (use_twopass ? kClsC4 : kClsC2);
+  }
   bool giant_direct = false;   // CVB_GIANT_DIRECT=1: giant entries go straight to the global tables
   bool use_first_sweep = true; // cvb env CVB_NO_FIRST_SWEEP=1 disables the singleton fast path
   bool rows_simple = false;    // every row holds each tail at most once (ascending)
@@ -351,16 +371,77 @@ int launch_cluster(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, cons
   return CVB_OK;
 }
 
+// ---- second-generation kernels (lm.cuh) ----------------------------------------
+// dynamic shared memory opt-in (once per device) and resident blocks per SM of a kernel
+static int lm_setup(cvb_engine *e, const void *kernel, int threads, size_t smem) {
+  static std::mutex m;
+  static std::map<std::pair<int, const void *>, int> occ;
+  std::lock_guard<std::mutex> lock(m);
+  auto it = occ.find({e->device, kernel});
+  if (it != occ.end()) return it->second;
+  if (smem > 40 * 1024 &&  // static shared memory counts against the 48 KB default too
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+    return -1;
+  int blocks = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, threads, smem) != cudaSuccess || blocks < 1)
+    return -1;
+  occ[{e->device, kernel}] = blocks;
+  return blocks;
+}
+
+template <int G, int U, int CAPLOG2>
+int launch_lm_group(cvb_engine *e, cudaStream_t st, const LmParams &p, int64_t first, int64_t n) {
+  if (n <= 0) return CVB_OK;
+  constexpr int NG = 32 / G;
+  constexpr size_t smem = lm_group_smem<G, U, CAPLOG2>();
+  auto go = [&](auto kern) -> int {
+    const int occ = lm_setup(e, reinterpret_cast<const void *>(kern), 256, smem);
+    CVB_CHECK(occ > 0, CVB_ERR_CUDA, "lm group kernel <%d,%d,%d>: cannot configure (%s)", G, U, CAPLOG2,
+              cudaGetErrorString(cudaGetLastError()));
+    int64_t grid = ((n + NG - 1) / NG + 7) / 8;
+    const int64_t cap = static_cast<int64_t>(e->num_sms) * occ;
+    if (grid > cap) grid = cap;
+    kern<<<static_cast<int>(grid), 256, smem, st>>>(p, static_cast<int>(first), static_cast<int>(n));
+    e->launches++;
+    return CVB_OK;
+  };
+  return e->unit_weights ? go(k_lm_group<G, U, CAPLOG2, true>) : go(k_lm_group<G, U, CAPLOG2, false>);
+}
+
+template <int TPV, int CAPLOG2>
+int launch_lm_block(cvb_engine *e, cudaStream_t st, const LmParams &p, int64_t first, int64_t n) {
+  if (n <= 0) return CVB_OK;
+  constexpr size_t smem = lm_block_smem<TPV, CAPLOG2>();
+  static const bool v4 = [] { const char *s = getenv("CVB_LM4"); return !(s && s[0] == '0'); }();
+  auto go = [&](auto kern) -> int {
+    const int occ = lm_setup(e, reinterpret_cast<const void *>(kern), TPV, smem);
+    CVB_CHECK(occ > 0, CVB_ERR_CUDA, "lm block kernel <%d,%d>: cannot configure (%s)", TPV, CAPLOG2,
+              cudaGetErrorString(cudaGetLastError()));
+    int64_t grid = n;
+    const int64_t cap = static_cast<int64_t>(e->num_sms) * occ;
+    if (grid > cap) grid = cap;
+    kern<<<static_cast<int>(grid), TPV, smem, st>>>(p, static_cast<int>(first), static_cast<int>(n));
+    e->launches++;
+    return CVB_OK;
+  };
+  if (v4) return e->unit_weights ? go(k_lm_block4<TPV, CAPLOG2, true>) : go(k_lm_block4<TPV, CAPLOG2, false>);
+  return e->unit_weights ? go(k_lm_block<TPV, CAPLOG2, true>) : go(k_lm_block<TPV, CAPLOG2, false>);
+}
+
 // The CVB_WEIGHTS_U32 sweep: pack labels, then the degree-class kernels forked
 // over the auxiliary streams and joined back on the engine stream.
 int launch_sweep_u32(cvb_engine *e) {
   cudaStream_t st = e->stream;
+  const bool lm = e->use_lm && e->lm_ready;
+  const bool first_sweep = e->sweeps_in_phase == 0 && e->rows_simple && e->use_first_sweep;
+  const bool remap = lm && e->remap;
   k_pack_labels<<<grid_for(e->nvg, 256), 256, 0, st>>>(e->nvg, e->sweep_labels(), e->cdeg.p, e->csize.p,
-                                                       e->packed.p);
+                                                       e->packed.p, remap ? e->rank.p : nullptr);
   e->launches++;
   SweepU32Params p;
   p.offsets = e->offsets.p;
-  p.tails = e->tails.p;
+  p.tails = remap ? e->tails_r.p : e->tails.p;
+  p.rank = remap ? e->rank.p : nullptr;
   p.weights = reinterpret_cast<const uint32_t *>(e->weights.p);
   p.packed = e->packed.p;
   p.cdeg = e->cdeg.p;
@@ -383,7 +464,24 @@ int launch_sweep_u32(cvb_engine *e) {
   auto cnt = [&](int c) { return e->class_start[c + 1] - e->class_start[c]; };
   auto lst = [&](int c) { return e->list.p + e->class_start[c]; };
   int64_t n;
-  if (e->sweeps_in_phase == 0 && e->rows_simple && e->use_first_sweep) {
+  LmParams q{};
+  if (lm) {
+    q.vrec = e->vrec.p;
+    q.tails = remap ? e->tails_r.p : e->tails.p;
+    q.remap = remap ? 1 : 0;
+    q.rank_top = static_cast<int>(e->nvl - 1);
+    q.weights = reinterpret_cast<const uint32_t *>(e->weights.p);
+    q.packed = e->packed.p;
+    q.selfw = e->has_selfloops ? e->selfw.p : nullptr;
+    q.constant = e->constant;
+    q.base = static_cast<vid_t>(e->base);
+    q.target = p.target;
+    q.cw = p.cw;
+    q.ddeg = p.ddeg;
+    q.dsize = p.dsize;
+  }
+  auto pos = [&](int c) { return e->class_start[c]; };
+  if (first_sweep) {
     // singleton start: nothing to merge, table-free kernels (one launch per width)
     auto span = [&](int c0, int c1) { return e->class_start[c1 + 1] - e->class_start[c0]; };
     CVB_CUDA(cudaEventRecord(e->ev_fork, st));
@@ -398,10 +496,32 @@ int launch_sweep_u32(cvb_engine *e) {
       kern<<<static_cast<int>(grid), 256, 0, s2>>>(p, lst(c0), static_cast<int>(m));
       e->launches++;
     };
+    if (lm) {
+      auto gof = [&](auto kern_unit, auto kern_w, int threads, int vpb, int c0, int c1, cudaStream_t s2) {
+        const int64_t m = span(c0, c1);
+        if (m <= 0) return;
+        int64_t grid = (m + vpb - 1) / vpb;
+        const int64_t cap = static_cast<int64_t>(e->num_sms) * (2048 / threads);
+        if (grid > cap) grid = cap;
+        if (e->unit_weights)
+          kern_unit<<<static_cast<int>(grid), threads, 0, s2>>>(q, static_cast<int>(pos(c0)), static_cast<int>(m));
+        else
+          kern_w<<<static_cast<int>(grid), threads, 0, s2>>>(q, static_cast<int>(pos(c0)), static_cast<int>(m));
+        e->launches++;
+      };
+      gof(k_lm_first_block<512, true>, k_lm_first_block<512, false>, 512, 1, kClsH8K, kClsH16K, e->aux[0]);
+      gof(k_lm_first_block<128, true>, k_lm_first_block<128, false>, 128, 1, kClsH2K, kClsH4K, e->aux[0]);
+      gof(k_lm_first_group<32, true>, k_lm_first_group<32, false>, 256, 8, kClsH512, kClsH1K, e->aux[2]);
+      gof(k_lm_first_group<16, true>, k_lm_first_group<16, false>, 256, 16, kClsH256, kClsH256, e->aux[2]);
+      gof(k_lm_first_group<8, true>, k_lm_first_group<8, false>, 256, 32, kClsG32, kClsH128, e->aux[3]);
+      gof(k_lm_first_group<4, true>, k_lm_first_group<4, false>, 256, 64, kClsG8, kClsG16, e->aux[3]);
+      go(k_sweep_u32_first<1>, 1, kClsG4, kClsG4, e->aux[3]);
+    } else {
     go(k_sweep_u32_first<256>, 256, kClsH2K, kClsH16K, e->aux[0]);
     go(k_sweep_u32_first<32>, 32, kClsH256, kClsH1K, e->aux[2]);
     go(k_sweep_u32_first<8>, 8, kClsG16, kClsH128, e->aux[3]);
     go(k_sweep_u32_first<1>, 1, kClsG4, kClsG8, e->aux[3]);
+    }
     if ((n = span(kClsC2, kClsGiant)) > 0) {  // every vertex above 8192 entries: chunked over the grid
       GiantTables gt{};
       gt.chunk_owner = e->big_owner.p;
@@ -426,16 +546,38 @@ int launch_sweep_u32(cvb_engine *e) {
   for (int i = 0; i < cvb_engine::kAux; ++i) CVB_CUDA(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
   // hash classes: 8 CSR entries per thread, TPV = upper degree / 8 threads per vertex
   // stream 0: block-per-vertex classes, largest vertices first
+  if (lm) {
+    CVB_TRY((launch_lm_block<1024, 14>(e, e->aux[0], q, pos(kClsH16K), cnt(kClsH16K))));
+    CVB_TRY((launch_lm_block<512, 13>(e, e->aux[0], q, pos(kClsH8K), cnt(kClsH8K))));
+    CVB_TRY((launch_lm_block<256, 12>(e, e->aux[0], q, pos(kClsH4K), cnt(kClsH4K))));
+    CVB_TRY((launch_lm_block<128, 11>(e, e->aux[0], q, pos(kClsH2K), cnt(kClsH2K))));
+  } else {
   if ((n = cnt(kClsH16K)) > 0) CVB_TRY((launch_hash<1024, 4, 2, 1>(e, e->aux[0], p, lst(kClsH16K), n)));
   if ((n = cnt(kClsH8K)) > 0) CVB_TRY((launch_hash<512, 4, 2, 2>(e, e->aux[0], p, lst(kClsH8K), n)));
   if ((n = cnt(kClsH4K)) > 0) CVB_TRY((launch_hash<256, 4, 2, 4>(e, e->aux[0], p, lst(kClsH4K), n)));
   if ((n = cnt(kClsH2K)) > 0) CVB_TRY((launch_hash<128, 4, 2, 8>(e, e->aux[0], p, lst(kClsH2K), n)));
+  }
   // stream 1: vertices above 8192 entries.  Default: global (L2-resident) tables for all of
   // them; CVB_CLUSTER=1 routes 8193..65536 to thread-block clusters with the table in
   // distributed shared memory (correct, but DSMEM moves ~32 B per 4-byte atomic and
   // measured slower on B200 — DESIGN.md section 5).
   const int gcls = e->global_table_class();
-  if (!e->use_cluster && e->use_twopass && (n = cnt(kClsC2)) > 0) {
+  const bool mp = lm && e->mp_ready;
+  if (mp && (n = e->class_start[kClsGiant] - e->class_start[kClsC2]) > 0) {
+    constexpr size_t smem = lm_multipass_smem();
+    auto go = [&](auto kern) -> int {
+      const int occ = lm_setup(e, reinterpret_cast<const void *>(kern), 1024, smem);
+      CVB_CHECK(occ > 0, CVB_ERR_CUDA, "lm multipass kernel: cannot configure (%s)",
+                cudaGetErrorString(cudaGetLastError()));
+      const int grid = static_cast<int>(n < e->num_sms ? n : e->num_sms);
+      kern<<<grid, 1024, smem, e->aux[1]>>>(q, static_cast<int>(pos(kClsC2)), static_cast<int>(n), e->mp_off.p,
+                                            e->mp_stage.p, e->mp_redo.p);
+      e->launches++;
+      return CVB_OK;
+    };
+    CVB_TRY(e->unit_weights ? go(k_lm_multipass<true>) : go(k_lm_multipass<false>));
+  }
+  if (!mp && !e->use_cluster && e->use_twopass && (n = cnt(kClsC2)) > 0) {
     constexpr int kTwoPassSmem = 16384 * 8;
     if (first_use_on_device(e->device, reinterpret_cast<const void *>(&k_sweep_u32_twopass))) {
       CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_twopass, cudaFuncAttributeMaxDynamicSharedMemorySize, kTwoPassSmem));
@@ -444,7 +586,7 @@ int launch_sweep_u32(cvb_engine *e) {
     k_sweep_u32_twopass<<<grid, 1024, kTwoPassSmem, e->aux[1]>>>(p, lst(kClsC2), static_cast<int>(n));
     e->launches++;
   }
-  if (e->use_cluster) {
+  if (e->use_cluster && !mp) {
     if ((n = cnt(kClsC8)) > 0) CVB_TRY(launch_cluster<8>(e, e->aux[1], p, lst(kClsC8), n));
     if ((n = cnt(kClsC4)) > 0) CVB_TRY(launch_cluster<4>(e, e->aux[1], p, lst(kClsC4), n));
     if ((n = cnt(kClsC2)) > 0) CVB_TRY(launch_cluster<2>(e, e->aux[1], p, lst(kClsC2), n));
@@ -506,6 +648,26 @@ int launch_sweep_u32(cvb_engine *e) {
                                                                                          gt);
     e->launches += 1;
     }
+  }
+  if (lm) {
+    // stream 2: 129..512; stream 3: 5..128
+    CVB_TRY((launch_lm_block<64, 10>(e, e->aux[2], q, pos(kClsH1K), cnt(kClsH1K))));
+    CVB_TRY((launch_lm_group<32, 8, 9>(e, e->aux[2], q, pos(kClsH512), cnt(kClsH512))));
+    CVB_TRY((launch_lm_group<16, 8, 8>(e, e->aux[3], q, pos(kClsH256), cnt(kClsH256))));
+    CVB_TRY((launch_lm_group<8, 8, 7>(e, e->aux[3], q, pos(kClsH128), cnt(kClsH128))));
+    CVB_TRY((launch_lm_group<4, 8, 6>(e, e->aux[3], q, pos(kClsG32), cnt(kClsG32))));
+    CVB_TRY((launch_lm_group<4, 4, 5>(e, e->aux[3], q, pos(kClsG16), cnt(kClsG16))));
+    CVB_TRY((launch_lm_group<2, 4, 4>(e, e->aux[3], q, pos(kClsG8), cnt(kClsG8))));
+    if ((n = cnt(kClsG4)) > 0) {
+      k_sweep_u32_t4<<<static_cast<int>((n + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG4), (int)n);
+      e->launches++;
+    }
+    for (int i = 0; i < cvb_engine::kAux; ++i) {
+      CVB_CUDA(cudaEventRecord(e->ev_join[i], e->aux[i]));
+      CVB_CUDA(cudaStreamWaitEvent(st, e->ev_join[i], 0));
+    }
+    CVB_CUDA(cudaGetLastError());
+    return CVB_OK;
   }
   // stream 2: warp-level and sub-warp hash classes
   if ((n = cnt(kClsH1K)) > 0) CVB_TRY((launch_hash<64, 4, 2, 16>(e, e->aux[2], p, lst(kClsH1K), n)));
@@ -644,10 +806,57 @@ int post_graph(cvb_engine *e) {
                                                                                      e->d_flags.p);
       e->launches++;
     }
-    int not_simple = 0;
-    CVB_CUDA(cudaMemcpyAsync(&not_simple, e->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    // lm.cuh: self-loop weights, unit-weight flag, per-vertex records in class-list order
+    e->lm_ready = false;
+    if (e->use_lm && e->nvl > 0 && e->ne < (int64_t(1) << 32)) {
+      CVB_TRY(e->selfw.ensure(e->nvl + 1));
+      CVB_TRY(e->vrec.ensure(e->nvl + 1));
+      k_self_loops<<<static_cast<int>((e->nvl * 32 + 255) / 256), 256, 0, st>>>(
+          e->offsets.p, e->tails.p, reinterpret_cast<const uint32_t *>(e->weights.p), e->nvl,
+          static_cast<vid_t>(e->base), e->selfw.p, e->d_flags.p);
+      k_build_vrec<<<grid_for(e->nvl, 256), 256, 0, st>>>(e->list.p, e->offsets.p, e->vdeg.p, e->nvl, e->vrec.p);
+      e->launches += 2;
+      e->lm_ready = true;
+    }
+    // multi-pass kernel (8193..65536 entries): staging area + per-vertex offsets
+    e->mp_ready = false;
+    if (e->lm_ready && e->use_mp) {
+      const int64_t nmp = e->class_start[kClsGiant] - e->class_start[kClsC2];
+      int64_t ent = 0;
+      for (int c = kClsC2; c < kClsGiant; ++c) ent += e->class_entries[c];
+      if (nmp > 0) {
+        CVB_TRY(e->mp_stage.ensure(static_cast<size_t>(ent) + 1));
+        CVB_TRY(e->mp_off.ensure(nmp + 1));
+        CVB_TRY(e->mp_deg.ensure(nmp + 1));
+        CVB_TRY(e->mp_redo.ensure(4));
+        CVB_CUDA(cudaMemsetAsync(e->mp_redo.p, 0, 4 * sizeof(int), st));
+        k_mp_degrees<<<grid_for(nmp, 256), 256, 0, st>>>(e->vrec.p + e->class_start[kClsC2], static_cast<int>(nmp),
+                                                        e->mp_deg.p);
+        size_t tb = 0;
+        CVB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, e->mp_deg.p, e->mp_off.p, static_cast<int>(nmp), st));
+        CVB_TRY(e->staging2.ensure(tb + 16));
+        CVB_CUDA(cub::DeviceScan::ExclusiveSum(e->staging2.p, tb, e->mp_deg.p, e->mp_off.p, static_cast<int>(nmp), st));
+        e->launches += 2;
+      }
+      e->mp_ready = true;
+    }
+    // degree-ordered gather layout: one GPU only (the class list covers every global vertex)
+    e->remap = false;
+    if (e->lm_ready && e->use_remap && e->nvl == e->nvg) {
+      CVB_TRY(e->rank.ensure(e->nvg + 1));
+      CVB_TRY(e->tails_r.ensure(static_cast<size_t>(e->ne) + 1));
+      k_rank_from_list<<<grid_for(e->nvl, 256), 256, 0, st>>>(e->list.p, e->nvl, e->rank.p);
+      if (e->ne > 0)
+        k_remap_tails<<<grid_for(e->ne, 256), 256, 0, st>>>(e->tails.p, e->rank.p, e->ne, e->tails_r.p);
+      e->launches += 2;
+      e->remap = true;
+    }
+    int hflags[4] = {0, 0, 0, 0};
+    CVB_CUDA(cudaMemcpyAsync(hflags, e->d_flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CVB_CUDA(cudaStreamSynchronize(st));
-    e->rows_simple = not_simple == 0;
+    e->rows_simple = hflags[0] == 0;
+    e->has_selfloops = hflags[1] != 0;
+    e->unit_weights = e->lm_ready && hflags[2] == 0;
     e->big_chunks = 0;
     if (nbig > 0) {  // chunk layout over every vertex above 8192 entries (first-sweep kernels)
       CVB_TRY(e->big_layout.ensure(2 * (nbig + 1)));
@@ -827,6 +1036,9 @@ cvb_engine *cvb_create(void *stream) {
   if (const char *s = getenv("CVB_NO_TWOPASS")) e->use_twopass = (s[0] != '1');
   if (const char *s = getenv("CVB_L2_PERSIST")) e->l2_persist = (s[0] == '1');
   if (const char *s = getenv("CVB_SPLIT")) e->use_split = (s[0] == '1');
+  if (const char *s = getenv("CVB_LM")) e->use_lm = (s[0] != '0');
+  if (const char *s = getenv("CVB_REMAP")) e->use_remap = (s[0] != '0');
+  if (const char *s = getenv("CVB_MP")) e->use_mp = (s[0] != '0');
   if (const char *s = getenv("CVB_BIG_DENSE")) e->big_dense = (s[0] != '0');
   if (const char *s = getenv("CVB_BIG_DENSE_MB")) {
     const long mb = atol(s);
@@ -874,7 +1086,8 @@ void cvb_destroy(cvb_engine *e) {
   e->partials.release(); e->d_sums.release(); e->ticket.release(); e->d_flags.release();
   e->h_sums.release(); e->staging.release(); e->staging2.release(); e->giant.release(); e->h_stage.release();
   e->packed.release(); e->giant_layout.release(); e->gslots.release(); e->pair_keys.release(); e->pair_w.release();
-  e->cdeg32.release();
+  e->cdeg32.release(); e->vrec.release(); e->selfw.release(); e->rank.release(); e->tails_r.release();
+  e->mp_stage.release(); e->mp_off.release(); e->mp_deg.release(); e->mp_redo.release();
   e->dense.release(); e->kcount.release(); e->klist.release(); e->gchunk2_gain.release(); e->gchunk2_key.release();
   e->gmeta.release(); e->gpiece_key.release(); e->gpiece_gain.release(); e->gchunk_gain.release();
   e->gchunk_key.release(); e->gchunk_owner.release(); e->big_layout.release(); e->big_owner.release();

@@ -1,0 +1,989 @@
+// lm.cuh — second-generation local-move kernels for CVB_WEIGHTS_U32 graphs.
+//
+// Same semantics as sweep_u32.cuh (distExecuteLouvainIteration /
+// distBuildLocalMapCounter / distGetMaxIndex, louvain.cpp:2185-2431; all sums
+// exact integers, so the result is independent of accumulation order), but
+// organised around the measured cost of the first generation: ~160 SASS
+// instructions per CSR entry, issue bound at one sixth of the HBM roofline.
+//
+// What changed, and why:
+//   * On R-MAT the neighbour communities of a vertex stay ~99 % DISTINCT in
+//     every sweep of phase 0 (measured with the oracle), so the table rarely
+//     merges anything and every entry ends in a gain evaluation.  The kernels
+//     are therefore two lean dynamic loops per vertex — insert, evaluate —
+//     instead of K-way unrolled register claims.
+//   * A vertex is described by ONE 16-byte record in class-list order
+//     (vertex, first entry, degree, vertex degree), read with one coalesced
+//     128-bit load; the self-loop weight is precomputed per phase, and the
+//     vertex's own community is pre-claimed in the table, so the insert loop
+//     carries no "own community" / "self loop" bookkeeping per entry.
+//   * Table slots are interleaved {key, weight} 8-byte records (one CAS and
+//     one RED at the same address; evaluation reads a slot with one LDS.64
+//     and frees it with one STS.64).  The lane that claims a slot appends
+//     {slot address, community degree} to its own list segment, so the
+//     evaluation loop touches exactly the claimed slots with full lanes and
+//     needs no gather: the community degree travelled with the label in the
+//     8-byte `packed` record.
+//   * Unit-weight graphs (every level-0 BASELINE config) never read the
+//     weights array.
+#pragma once
+
+#include "common.cuh"
+#include "sweep_u32.cuh"
+
+namespace cvb {
+
+// Per-vertex record, stored in degree-class list order.
+struct __align__(16) VertexRec {
+  vid_t v;          // local vertex id
+  uint32_t e0;      // first CSR entry (graphs on this path hold < 2^32 entries per GPU)
+  uint32_t deg;     // number of entries
+  uint32_t vdeg;    // weighted degree (exact integer < 2^32)
+};
+
+struct LmParams {
+  const VertexRec *__restrict__ vrec;   // [nv_local] in class-list order
+  const vid_t *__restrict__ tails;      // [ne]
+  const uint32_t *__restrict__ weights; // [ne] (not read by UNIT kernels)
+  const uint2 *__restrict__ packed;     // [nv_global] {label | singleton<<31, degree of that community}
+  const uint32_t *__restrict__ selfw;   // [nv_local] self-loop weight per vertex; nullptr when the graph has none
+  double constant;
+  vid_t base;
+  // degree-ordered gather layout: when remap != 0, `tails` holds RANKS (position of the tail in the
+  // degree-class list, biggest classes first) and packed[] is indexed by rank, so the records of the
+  // high-degree vertices — the ones most entries point to — are contiguous and stay in L1/L2.  The
+  // vertex at class-list position i has rank rank_top - i.
+  int remap;
+  int rank_top;
+  vid_t *__restrict__ target;  // [nv_local]
+  double *__restrict__ cw;     // [nv_local]
+  double *__restrict__ ddeg;   // [nv_global] or nullptr (labels-only exchange)
+  int32_t *__restrict__ dsize; // [nv_global]
+};
+
+// index of a vertex's own record in packed[] (and the value its self-loop entries carry in tails[])
+__device__ __forceinline__ uint32_t lm_self(const LmParams &p, uint32_t v, int list_pos) {
+  return p.remap ? static_cast<uint32_t>(p.rank_top - list_pos) : v + static_cast<uint32_t>(p.base);
+}
+
+// rank[v] = nv-1 - (position of v in the degree-class list): one thread per list position (one GPU: nv_local == nv_global)
+__global__ void k_rank_from_list(const vid_t *__restrict__ list, int64_t nv, vid_t *__restrict__ rank) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    rank[list[i]] = static_cast<vid_t>(nv - 1 - i);
+}
+
+__global__ void k_remap_tails(const vid_t *__restrict__ tails, const vid_t *__restrict__ rank, int64_t ne,
+                              vid_t *__restrict__ tails_r) {
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < ne;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    tails_r[e] = rank[tails[e]];
+}
+
+// ---- per-phase setup ---------------------------------------------------------
+__global__ void k_build_vrec(const vid_t *__restrict__ list, const eid_t *__restrict__ offsets,
+                             const double *__restrict__ vdeg, int64_t nv, VertexRec *__restrict__ vrec) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const vid_t v = list[i];
+    const eid_t e0 = offsets[v];
+    VertexRec r;
+    r.v = v;
+    r.e0 = static_cast<uint32_t>(e0);
+    r.deg = static_cast<uint32_t>(offsets[v + 1] - e0);
+    r.vdeg = static_cast<uint32_t>(vdeg[v]);
+    vrec[i] = r;
+  }
+}
+
+// selfw[v] = sum of the weights of v's entries whose tail is v itself; flags[1] |= 1 when any is non-zero,
+// flags[2] |= 1 when some weight differs from 1.  One warp per vertex.
+__global__ void k_self_loops(const eid_t *__restrict__ offsets, const vid_t *__restrict__ tails,
+                             const uint32_t *__restrict__ weights, int64_t nv, vid_t base,
+                             uint32_t *__restrict__ selfw, int *__restrict__ flags) {
+  const int64_t v = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  if (v >= nv) return;
+  const vid_t self = static_cast<vid_t>(v) + base;
+  uint32_t s = 0u;
+  int nonunit = 0;
+  for (eid_t e = offsets[v] + lane; e < offsets[v + 1]; e += 32) {
+    const uint32_t w = weights[e];
+    if (tails[e] == self) s += w;
+    nonunit |= (w != 1u);
+  }
+  s = __reduce_add_sync(0xffffffffu, s);
+  nonunit = __any_sync(0xffffffffu, nonunit);
+  if (lane == 0) {
+    selfw[v] = s;
+    if (s) atomicOr(&flags[1], 1);
+    if (nonunit) atomicOr(&flags[2], 1);
+  }
+}
+
+// ---- small PTX helpers (32-bit shared addresses) ---------------------------------
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts64_if(bool pred, uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.shared.v2.u32 [%0], {%1, %2};\n\t}" ::"r"(addr),
+               "r"(a), "r"(b), "r"(static_cast<uint32_t>(pred))
+               : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// byte offset of a key's home slot in a table of 2^CAPLOG2 8-byte slots
+template <int CAPLOG2>
+__device__ __forceinline__ uint32_t lm_home(uint32_t key) {
+  // Fibonacci hashing: the TOP bits of the low 32-bit product (labels are small integers, so
+  // the high word of the 64-bit product would keep consecutive labels in consecutive slots)
+  return ((key * 0x9E3779B1u) >> (29 - CAPLOG2)) & (((1u << CAPLOG2) - 1u) << 3);
+}
+
+__device__ __forceinline__ bool lm_better(double g2, uint32_t k2, double g, uint32_t k) {
+  return (g2 > g) || (g2 == g && (k2 & kLabelMask) < (k & kLabelMask));
+}
+
+// louvain.cpp:2240-2241 (two singletons only merge towards the smaller id), 2294, 2381 and the
+// Cupdate deltas of 2307-2376.
+__device__ __forceinline__ void lm_commit(const LmParams &p, vid_t v, uint32_t me_key, double best_gain,
+                                          uint32_t best_key, double vd, double counter0) {
+  const vid_t cc = static_cast<vid_t>(me_key & kLabelMask);
+  vid_t best = (best_gain > 0.0) ? static_cast<vid_t>(best_key & kLabelMask) : cc;
+  if (best != cc && best > cc && (best_key & kSingletonBit) && (me_key & kSingletonBit)) best = cc;
+  p.target[v] = best;
+  p.cw[v] = counter0;
+  if (best != cc && p.ddeg != nullptr) {
+    atomicAdd(&p.ddeg[best], vd);
+    atomicAdd(&p.dsize[best], 1);
+    atomicAdd(&p.ddeg[cc], -vd);
+    atomicAdd(&p.dsize[cc], -1);
+  }
+}
+
+// Per-lane list segment: U records (U = the most entries a lane owns) of 8 bytes, record j of
+// a lane at lst0 + j*lstride.
+//   * claim records {slot address, community degree} grow UP from record 0: one per table slot this
+//     lane opened — the evaluation loop walks exactly these;
+//   * deferred records {key, community degree} (unit weights) or {key, position in the row}
+//     (weighted graphs: weight and degree are re-read, they are cache hits) grow DOWN from record
+//     U-1: entries whose first probe hit a slot owned by another community.  They are resolved after
+//     the unrolled claims (lm_resolve_deferred), every lane walking its own short queue, so that a
+//     collision costs its own lane a few probes instead of stalling the other 31 lanes inside the
+//     unrolled code (measured: inline probe loops tripled the executed instructions).
+// An entry produces at most one record, so the two ends never meet.
+//
+// One lane owns the entries lane_pos, lane_pos+stride, ... (at most U of them) of a row and handles
+// them in ONE round: all streaming loads, then all gathers, then all first-probe claims are in
+// flight together, so a vertex costs one global round trip for the tails and one for the gather
+// (the first version walked blocks of 4, 2 and 1 entries: three serialised round trips, and the
+// profile showed the kernel waiting on memory with the issue slots 25 % busy).
+template <int CAPLOG2, int U, bool UNIT>
+__device__ __forceinline__ void lm_insert_lane(const LmParams &p, const vid_t *__restrict__ row,
+                                               const uint32_t *__restrict__ wrow, int lane_pos, int stride, int deg,
+                                               uint32_t tbl, int lstride, uint32_t &front, uint32_t back0) {
+  uint32_t back = back0;
+  uint32_t tail[U], w[U], so[U], old[U];
+  uint2 pk[U];
+  // number of entries of this lane: idx = lane_pos + u*stride < deg
+  int nv = (deg - lane_pos + stride - 1) / stride;
+  nv = nv < 0 ? 0 : (nv > U ? U : nv);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    tail[u] = 0u;
+    w[u] = 1u;
+    if (u < nv) {
+      tail[u] = static_cast<uint32_t>(__ldcs(row + lane_pos + u * stride));
+      if (!UNIT) w[u] = __ldcs(wrow + lane_pos + u * stride);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u < nv) pk[u] = __ldg(&p.packed[tail[u]]);
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u < nv) {
+      so[u] = tbl + lm_home<CAPLOG2>(pk[u].x);
+      old[u] = atoms_cas(so[u], kEmptyKeyU, pk[u].x);
+    }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u < nv) {
+      const bool fresh = old[u] == kEmptyKeyU;
+      const bool pend = !fresh && old[u] != pk[u].x;
+      // a deferred entry adds to a private scratch word instead (its own unused claim record)
+      reds_add(pend ? front + 4u : so[u] + 4u, w[u]);
+      sts64_if(fresh, front, so[u], pk[u].y);
+      front += fresh ? lstride : 0;
+      sts64_if(pend, back, pk[u].x, UNIT ? pk[u].y : static_cast<uint32_t>(lane_pos + u * stride));
+      back -= pend ? lstride : 0;
+    }
+  // deferred entries, most recent first (so a claim record written at the front never lands on an
+  // unread deferred record): double hashing from the home slot
+  constexpr uint32_t kMaskB = ((1u << CAPLOG2) - 1u) << 3;
+  for (uint32_t a = back + lstride; a != back0 + lstride; a += lstride) {
+    const uint2 r = lds64(a);
+    const uint32_t key = r.x;
+    uint32_t ay = r.y, wd = 1u;
+    if (!UNIT) {
+      wd = __ldg(wrow + r.y);
+      ay = __ldg(&p.packed[__ldg(row + r.y)]).y;
+    }
+    uint32_t s2 = lm_home<CAPLOG2>(key);
+    const uint32_t step = (((key * 0x85EBCA6Bu) >> (29 - CAPLOG2)) & kMaskB) | 8u;  // odd number of slots
+    uint32_t o2;
+    do {
+      s2 = (s2 + step) & kMaskB;
+      o2 = atoms_cas(tbl + s2, kEmptyKeyU, key);
+    } while (o2 != kEmptyKeyU && o2 != key);
+    reds_add(tbl + s2 + 4u, wd);
+    if (o2 == kEmptyKeyU) {
+      sts64(front, tbl + s2, ay);
+      front += lstride;
+    }
+  }
+}
+
+// Evaluate the claims of one lane: records lst0, lst0+lstride, ... (exclusive lst_end).
+__device__ __forceinline__ void lm_eval(uint32_t lst0, uint32_t lst_end, int lstride, double eix, double vd, double ax,
+                                        double constant, double &g, uint32_t &id) {
+  for (uint32_t a = lst0; a != lst_end; a += lstride) {
+    const uint2 rec = lds64(a);        // {slot address, community degree}
+    const uint2 kw = lds64(rec.x);     // {community | singleton bit, accumulated weight}
+    sts64(rec.x, kEmptyKeyU, 0u);      // free the slot for the next vertex
+    const double g2 = modularity_gain(u32_to_f64(kw.y), eix, vd, u32_to_f64(rec.y), ax, constant);
+    if (lm_better(g2, kw.x, g, id)) {
+      g = g2;
+      id = kw.x;
+    }
+  }
+}
+
+// full-warp xor-shuffle argmax inside aligned groups of G lanes (offsets < G never leave a group; a
+// per-group mask would make the compiler serialise the shuffles group by group)
+template <int G>
+__device__ __forceinline__ uint32_t lm_group_argmax(double g, uint32_t key, double *gain_out) {
+  if (G == 32) return warp_argmax(g, key, gain_out, 0xffffffffu);
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const double g2 = __shfl_xor_sync(0xffffffffu, g, o);
+    const uint32_t k2 = __shfl_xor_sync(0xffffffffu, key, o);
+    if (lm_better(g2, k2, g, key)) {
+      g = g2;
+      key = k2;
+    }
+  }
+  *gain_out = g;
+  return key;
+}
+
+// ---------------------------------------------------------------------------
+// G lanes per vertex (G = 2 .. 32), at most U entries per lane (degree <= G*U),
+// 32/G vertices per warp, 8 warps per block; table of 2^CAPLOG2 >= 2*G*U slots
+// per vertex plus G*U list records.  Persistent warps stride over batches of
+// 32/G consecutive class-list positions.
+// Shared memory per vertex: 8 * CAP (table) + 8 * G * U (lists).
+// ---------------------------------------------------------------------------
+template <int G, int U, int CAPLOG2>
+__host__ __device__ constexpr size_t lm_group_smem() {
+  return static_cast<size_t>(8) * (32 / G) * ((8u << CAPLOG2) + 8u * G * U);
+}
+
+template <int G, int U, int CAPLOG2, bool UNIT>
+__global__ void __launch_bounds__(256, 4) k_lm_group(LmParams p, int first, int n) {
+  constexpr int NG = 32 / G;
+  constexpr int CAP = 1 << CAPLOG2;
+  static_assert(CAP >= 2 * G * U, "table too small for the class");
+  constexpr uint32_t kTblBytes = CAP * 8u, kListBytes = G * U * 8u;
+  constexpr int LSTRIDE = G * 8;
+  extern __shared__ __align__(16) unsigned char lm_smem[];
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = static_cast<int>(threadIdx.x >> 5);
+  const int grp = static_cast<int>(lane) / G, lig = static_cast<int>(lane) % G;
+  const uint32_t smem0 = smem_addr(lm_smem);
+  const uint32_t tbl = smem0 + static_cast<uint32_t>(wib * NG + grp) * kTblBytes;
+  const uint32_t lst0 = smem0 + 8u * NG * kTblBytes + static_cast<uint32_t>(wib * NG + grp) * kListBytes +
+                        static_cast<uint32_t>(lig) * 8u;
+  const uint32_t back0 = lst0 + (U - 1) * LSTRIDE;
+  for (int s = lig; s < CAP; s += G) sts64(tbl + s * 8u, kEmptyKeyU, 0u);
+  __syncwarp();
+
+  const int nbatch = (n + NG - 1) / NG;
+  for (int b = blockIdx.x * 8 + wib; b < nbatch; b += gridDim.x * 8) {
+    const int item = b * NG + grp;
+    const bool live = item < n;
+    const uint4 r4 = live ? __ldg(reinterpret_cast<const uint4 *>(p.vrec + first + item)) : make_uint4(0u, 0u, 0u, 0u);
+    const vid_t v = static_cast<vid_t>(r4.x);
+    const int deg = static_cast<int>(r4.z);
+    const uint32_t self = live ? lm_self(p, r4.x, first + item) : 0u;
+    const uint2 me = __ldg(&p.packed[self]);
+    const uint32_t hcc = tbl + lm_home<CAPLOG2>(me.x);
+    if (live && lig == 0) sts_u32(hcc, me.x);  // pre-claim the own community: counter[0] lives in its home slot
+    __syncwarp();
+    uint32_t lst = lst0;
+    lm_insert_lane<CAPLOG2, U, UNIT>(p, p.tails + r4.y, p.weights + r4.y, lig, G, deg, tbl, LSTRIDE, lst, back0);
+    __syncwarp();
+    const double vd = u32_to_f64(r4.w);
+    const double counter0 = u32_to_f64(lds_u32(hcc + 4u));
+    double eix = counter0;
+    if (p.selfw != nullptr && live) eix = counter0 - u32_to_f64(__ldg(&p.selfw[v]));
+    const double ax = u32_to_f64(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+    lm_eval(lst0, lst, LSTRIDE, eix, vd, ax, p.constant, g, id);
+    double wg;
+    const uint32_t wid = lm_group_argmax<G>(g, id, &wg);
+    if (live && lig == 0) {
+      lm_commit(p, v, me.x, wg, wid, vd, counter0);
+      sts64(hcc, kEmptyKeyU, 0u);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// One block per vertex, 8 entries per thread: a vertex of degree d is worked on by the first
+// ceil(d/8) threads rounded up to whole warps (the other warps of the block skip to the barrier),
+// so every active lane owns 8 entries except in the last stride.  Table of 2^CAPLOG2 >= 16*TPV
+// slots, one 8-record list segment per thread.  The record and the own packed entry of the NEXT
+// vertex are fetched while the current one is processed.
+// Shared memory: 8 * CAP (table) + 64 * TPV (lists).
+// ---------------------------------------------------------------------------
+template <int TPV, int CAPLOG2>
+__host__ __device__ constexpr size_t lm_block_smem() {
+  return (static_cast<size_t>(8) << CAPLOG2) + static_cast<size_t>(64) * TPV;
+}
+
+template <int TPV, int CAPLOG2, bool UNIT>
+__global__ void __launch_bounds__(TPV, 1024 / TPV) k_lm_block(LmParams p, int first, int n) {
+  constexpr int CAP = 1 << CAPLOG2;
+  constexpr int U = 8;
+  static_assert(CAP >= 2 * TPV * U, "table too small for the class");
+  constexpr uint32_t kTblBytes = CAP * 8u;
+  constexpr int kWarps = TPV / 32;
+  extern __shared__ __align__(16) unsigned char lm_smem[];
+  __shared__ double red_g[kWarps];
+  __shared__ uint32_t red_id[kWarps];
+  const int tid = static_cast<int>(threadIdx.x);
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = tid >> 5;
+  const uint32_t tbl = smem_addr(lm_smem);
+  for (int s = tid; s < CAP; s += TPV) sts64(tbl + s * 8u, kEmptyKeyU, 0u);
+  __syncthreads();
+
+  int item = blockIdx.x;
+  if (item >= n) return;
+  uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(p.vrec + first + item));
+  uint2 me = __ldg(&p.packed[lm_self(p, r4.x, first + item)]);
+  for (; item < n; item += gridDim.x) {
+    // prefetch the next vertex of this block
+    const int nitem = item + gridDim.x;
+    uint4 r4n = r4;
+    uint2 men = me;
+    if (nitem < n) {
+      r4n = __ldg(reinterpret_cast<const uint4 *>(p.vrec + first + nitem));
+      men = __ldg(&p.packed[lm_self(p, r4n.x, first + nitem)]);
+    }
+    const vid_t v = static_cast<vid_t>(r4.x);
+    const int deg = static_cast<int>(r4.z);
+    int act = (((deg + U - 1) / U) + 31) & ~31;  // threads working on this vertex (whole warps)
+    act = act > TPV ? TPV : act;
+    const uint32_t hcc = tbl + lm_home<CAPLOG2>(me.x);
+    if (tid == 0) sts_u32(hcc, me.x);
+    __syncthreads();
+    const int lstride = act * 8;
+    const uint32_t lst0 = tbl + kTblBytes + static_cast<uint32_t>(tid) * 8u;
+    uint32_t lst = lst0;
+    if (tid < act)
+      lm_insert_lane<CAPLOG2, U, UNIT>(p, p.tails + r4.y, p.weights + r4.y, tid, act, deg, tbl, lstride, lst,
+                                       lst0 + (U - 1) * lstride);
+    __syncthreads();
+    const double vd = u32_to_f64(r4.w);
+    const double counter0 = u32_to_f64(lds_u32(hcc + 4u));
+    double eix = counter0;
+    if (p.selfw != nullptr) eix = counter0 - u32_to_f64(__ldg(&p.selfw[v]));
+    const double ax = u32_to_f64(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+    lm_eval(lst0, lst, lstride, eix, vd, ax, p.constant, g, id);
+    double wg;
+    uint32_t wid = warp_argmax(g, id, &wg);
+    if (lane == 0) {
+      red_g[wib] = wg;
+      red_id[wib] = wid;
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 1; i < kWarps; ++i)
+        if (lm_better(red_g[i], red_id[i], wg, wid)) {
+          wg = red_g[i];
+          wid = red_id[i];
+        }
+      lm_commit(p, v, me.x, wg, wid, vd, counter0);
+      sts64(hcc, kEmptyKeyU, 0u);
+    }
+    // thread 0 pre-claims the next vertex after its own commit; everyone else meets it at the
+    // barrier that follows the pre-claim, so red_g/red_id are not overwritten early
+    r4 = r4n;
+    me = men;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Fourth-generation block kernel (the default for 257..8192 entries).
+//
+// What the profile of the previous versions said (profiles/r02_lm_v2_*): the L1TEX pipe — random
+// gathers at ~1 sector/clk/SM plus the shared-memory accesses, ~3.6 clk per random 32-bit warp access —
+// is the resource that bounds the sweep, and the issue slots were 25 % busy because every vertex
+// serialised tails -> gather -> claims -> barrier -> evaluation.  So this version
+//   * keeps the claims of a lane in REGISTERS: the lane that opens a community's home slot with its
+//     first probe remembers (community, degree) and, after the barrier, reads the slot's accumulated
+//     weight, evaluates the gain and frees the slot — no claim list is written or read for them;
+//   * on unit-weight graphs a claim adds nothing: the slot's weight word only counts LATER entries of
+//     the same community (total = 1 + count), so the common case costs one CAS, one LDS and one STS;
+//   * resolves first-probe collisions after the unrolled claims (deferred records, double hashing);
+//     slots opened there are recorded {slot address, degree} and evaluated from the record;
+//   * is software-pipelined across vertices: the tails and the packed records of vertex k+1 are loaded
+//     while vertex k is claimed, evaluated and committed.
+// Per-lane list segment (8 records of 8 bytes): claim records grow up, deferred records grow down; an
+// entry produces at most one record.
+// ---------------------------------------------------------------------------
+template <int TPV, int CAPLOG2>
+__host__ __device__ constexpr size_t lm_block4_smem() {
+  return (static_cast<size_t>(8) << CAPLOG2) + static_cast<size_t>(64) * TPV;
+}
+
+template <int TPV, int CAPLOG2, bool UNIT>
+__global__ void __launch_bounds__(TPV, (TPV >= 512 ? 1024 : 768) / TPV) k_lm_block4(LmParams p, int first, int n) {
+  constexpr int CAP = 1 << CAPLOG2;
+  constexpr int U = 8;
+  static_assert(CAP >= 2 * TPV * U, "table too small for the class");
+  constexpr uint32_t kTblBytes = CAP * 8u;
+  constexpr uint32_t kMaskB = ((1u << CAPLOG2) - 1u) << 3;
+  constexpr int kWarps = TPV / 32;
+  extern __shared__ __align__(16) unsigned char lm_smem[];
+  __shared__ double red_g[kWarps];
+  __shared__ uint32_t red_id[kWarps];
+  const int tid = static_cast<int>(threadIdx.x);
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = tid >> 5;
+  const uint32_t tbl = smem_addr(lm_smem);
+  const uint32_t lst0 = tbl + kTblBytes + static_cast<uint32_t>(tid) * 8u;
+  for (int s = tid; s < CAP; s += TPV) sts64(tbl + s * 8u, kEmptyKeyU, 0u);
+
+  int item = blockIdx.x;
+  if (item >= n) return;
+  // ---- pipeline prologue: record, own entry, tails and gathers of the first vertex ----
+  uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(p.vrec + first + item));
+  uint2 me = __ldg(&p.packed[lm_self(p, r4.x, first + item)]);
+  int nitem = item + gridDim.x;
+  uint4 r4n = r4;
+  if (nitem < n) r4n = __ldg(reinterpret_cast<const uint4 *>(p.vrec + first + nitem));
+  uint2 pk[U];
+  uint32_t w[U];
+  auto lanes_of = [](int deg) {
+    int a = (((deg + U - 1) / U) + 31) & ~31;  // whole warps, 8 entries per thread
+    return a > TPV ? TPV : a;
+  };
+  auto count_of = [&](int deg, int act) {
+    int c = (deg - tid + act - 1) / act;  // entries tid, tid+act, ... < deg
+    return (tid >= act || c < 0) ? 0 : (c > U ? U : c);
+  };
+  int act = lanes_of(static_cast<int>(r4.z));
+  int nv = count_of(static_cast<int>(r4.z), act);
+  {
+    uint32_t t[U];
+    const vid_t *__restrict__ row = p.tails + r4.y;
+    const uint32_t *__restrict__ wrow = p.weights + r4.y;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      t[u] = 0u;
+      w[u] = 1u;
+      if (u < nv) {
+        t[u] = static_cast<uint32_t>(__ldcs(row + tid + u * act));
+        if (!UNIT) w[u] = __ldcs(wrow + tid + u * act);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < nv) pk[u] = __ldg(&p.packed[t[u]]);
+  }
+  if (tid == 0) sts_u32(tbl + lm_home<CAPLOG2>(me.x), me.x);  // pre-claim the first vertex's own community
+
+  for (; item < n; item = nitem, nitem += gridDim.x) {
+    const vid_t v = static_cast<vid_t>(r4.x);
+    const int lstride = act * 8;
+    const uint32_t hcc = tbl + lm_home<CAPLOG2>(me.x);
+    // ---- A: record of vertex k+2, own entry and tails of vertex k+1 (in flight during the claims) ----
+    const bool has_next = nitem < n;
+    uint4 r4nn = r4n;
+    uint2 men = me;
+    int actn = 0, nvn = 0;
+    uint32_t tn[U], wn[U];
+    if (has_next) {
+      if (nitem + static_cast<int>(gridDim.x) < n)
+        r4nn = __ldg(reinterpret_cast<const uint4 *>(p.vrec + first + nitem + gridDim.x));
+      men = __ldg(&p.packed[lm_self(p, r4n.x, first + nitem)]);
+      actn = lanes_of(static_cast<int>(r4n.z));
+      nvn = count_of(static_cast<int>(r4n.z), actn);
+    }
+    {
+      const vid_t *__restrict__ rown = p.tails + r4n.y;
+      const uint32_t *__restrict__ wrown = p.weights + r4n.y;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        tn[u] = 0u;
+        wn[u] = 1u;
+        if (u < nvn) {
+          tn[u] = static_cast<uint32_t>(__ldcs(rown + tid + u * actn));
+          if (!UNIT) wn[u] = __ldcs(wrown + tid + u * actn);
+        }
+      }
+    }
+    __syncthreads();  // T: the own community is pre-claimed, every slot of the previous vertex is free
+    // ---- B: first-probe claims of this lane's entries ----
+    uint32_t front = lst0;                     // claim records grow up
+    uint32_t back = lst0 + (U - 1) * lstride;  // deferred records grow down
+    const uint32_t back0 = back;
+    uint32_t old[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < nv) old[u] = atoms_cas(tbl + lm_home<CAPLOG2>(pk[u].x), kEmptyKeyU, pk[u].x);
+    uint32_t freshmask = 0u;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < nv) {
+        const bool fresh = old[u] == kEmptyKeyU;
+        const bool same = old[u] == pk[u].x;
+        freshmask |= fresh ? (1u << u) : 0u;
+        // unit weights: the slot counts the entries AFTER the claim; weighted: every entry adds
+        if (UNIT ? same : (fresh || same)) reds_add(tbl + lm_home<CAPLOG2>(pk[u].x) + 4u, w[u]);
+        const bool pend = !fresh && !same;
+        sts64_if(pend, back, pk[u].x, UNIT ? pk[u].y : static_cast<uint32_t>(tid + u * act));
+        back -= pend ? lstride : 0;
+      }
+    // ---- C: gathers of vertex k+1 ----
+    uint2 pkn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < nvn) pkn[u] = __ldg(&p.packed[tn[u]]);
+    // ---- D: deferred entries, most recent first (a claim record written at the front never lands on an
+    //         unread deferred record): double hashing from the home slot ----
+    for (uint32_t a = back + lstride; a != back0 + lstride; a += lstride) {
+      const uint2 r = lds64(a);
+      const uint32_t key = r.x;
+      uint32_t ay = r.y, wd = 1u;
+      if (!UNIT) {
+        wd = __ldg(p.weights + r4.y + r.y);
+        ay = __ldg(&p.packed[__ldg(p.tails + r4.y + r.y)]).y;
+      }
+      uint32_t s2 = lm_home<CAPLOG2>(key);
+      const uint32_t step = (((key * 0x85EBCA6Bu) >> (29 - CAPLOG2)) & kMaskB) | 8u;  // odd number of slots
+      uint32_t o2;
+      do {
+        s2 = (s2 + step) & kMaskB;
+        o2 = atoms_cas(tbl + s2, kEmptyKeyU, key);
+      } while (o2 != kEmptyKeyU && o2 != key);
+      if (!UNIT || o2 == key) reds_add(tbl + s2 + 4u, wd);
+      if (o2 == kEmptyKeyU) {
+        sts64(front, tbl + s2, ay);
+        front += lstride;
+      }
+    }
+    __syncthreads();  // S1: every entry of the vertex is in the table
+    // ---- E: evaluation; each lane reads and frees the slots it opened ----
+    const double vd = u32_to_f64(r4.w);
+    const uint32_t c0u = lds_u32(hcc + 4u);
+    const double counter0 = u32_to_f64(c0u);
+    double eix = counter0;
+    if (p.selfw != nullptr) eix = counter0 - u32_to_f64(__ldg(&p.selfw[v]));
+    const double ax = u32_to_f64(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+    for (uint32_t a = lst0; a != front; a += lstride) {  // slots opened while resolving deferred entries
+      const uint2 rec = lds64(a);
+      const uint2 kw = lds64(rec.x);
+      sts64(rec.x, kEmptyKeyU, 0u);
+      const uint32_t tot = UNIT ? kw.y + 1u : kw.y;
+      const double g2 = modularity_gain(u32_to_f64(tot), eix, vd, u32_to_f64(rec.y), ax, p.constant);
+      if (lm_better(g2, kw.x, g, id)) {
+        g = g2;
+        id = kw.x;
+      }
+    }
+    uint32_t cnt[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (freshmask & (1u << u)) cnt[u] = lds_u32(tbl + lm_home<CAPLOG2>(pk[u].x) + 4u);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (freshmask & (1u << u)) {
+        const uint32_t so = tbl + lm_home<CAPLOG2>(pk[u].x);
+        if (UNIT) {
+          sts_u32(so, kEmptyKeyU);
+          if (cnt[u] != 0u) sts_u32(so + 4u, 0u);  // rare: a later entry of the same community
+        } else {
+          sts64(so, kEmptyKeyU, 0u);
+        }
+        const uint32_t tot = UNIT ? cnt[u] + 1u : cnt[u];
+        const double g2 = modularity_gain(u32_to_f64(tot), eix, vd, u32_to_f64(pk[u].y), ax, p.constant);
+        if (lm_better(g2, pk[u].x, g, id)) {
+          g = g2;
+          id = pk[u].x;
+        }
+      }
+    double wg;
+    uint32_t wid = warp_argmax(g, id, &wg);
+    if (lane == 0) {
+      red_g[wib] = wg;
+      red_id[wib] = wid;
+    }
+    __syncthreads();  // S2: all slots but the own community's are free again
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 1; i < kWarps; ++i)
+        if (lm_better(red_g[i], red_id[i], wg, wid)) {
+          wg = red_g[i];
+          wid = red_id[i];
+        }
+      lm_commit(p, v, me.x, wg, wid, vd, counter0);
+      sts64(hcc, kEmptyKeyU, 0u);
+      if (has_next) sts_u32(tbl + lm_home<CAPLOG2>(men.x), men.x);  // pre-claim the next vertex's own community
+    }
+    // ---- rotate the pipeline ----
+    r4 = r4n;
+    r4n = r4nn;
+    me = men;
+    act = actn;
+    nv = nvn;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      pk[u] = pkn[u];
+      w[u] = wn[u];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// 8193 .. 65536 entries: one 1024-thread block per vertex, the neighbour communities are
+// accumulated in P = 2..16 PASSES over the row, pass q taking the communities whose partition hash
+// is q, so that a 16384-slot shared-memory table (at most ~6144 expected communities per pass)
+// serves rows far beyond its own capacity — no global table, no L2 atomics (the first-generation
+// global-table path ran these vertices at 15 G entries/s, 4.3 of the 9.9 ms of a scale-24 sweep).
+// Pass 0 streams the tails, gathers the packed records and STAGES them next to the row in global
+// memory (8 bytes per entry, coalesced); later passes re-read the staged records instead of
+// gathering again: a coalesced 8-byte read costs a quarter of a random gather on the L1TEX pipe.
+// Claims are appended to a block-wide list {slot address, community degree} through a
+// warp-aggregated cursor and evaluated (and their slots freed) after every pass.  Should a pass
+// ever meet more communities than the list holds (the partition hash would have to be very
+// uneven), the vertex is redone with twice the passes.
+// Shared memory: 128 KB table + 64 KB claim list + 64 bytes.
+// ---------------------------------------------------------------------------
+constexpr int kMpCapLog2 = 14;
+constexpr int kMpListCap = 8192;
+constexpr int kMpTarget = 6144;  // expected communities per pass at most
+__host__ __device__ constexpr size_t lm_multipass_smem() {
+  return (static_cast<size_t>(8) << kMpCapLog2) + static_cast<size_t>(kMpListCap) * 8 + 64;
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(1024, 1) k_lm_multipass(LmParams p, int first, int n, const uint32_t *__restrict__ stage_off,
+                                                          uint2 *__restrict__ stage, int *__restrict__ redo_count) {
+  constexpr int TPB = 1024, CAP = 1 << kMpCapLog2, UB = 4;
+  constexpr uint32_t kTblBytes = CAP * 8u;
+  constexpr uint32_t kMaskB = (CAP - 1u) << 3;
+  extern __shared__ __align__(16) unsigned char lm_smem[];
+  __shared__ double red_g[32];
+  __shared__ uint32_t red_id[32];
+  const int tid = static_cast<int>(threadIdx.x);
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = tid >> 5;
+  const uint32_t tbl = smem_addr(lm_smem);
+  const uint32_t lst = tbl + kTblBytes;
+  const uint32_t meta = lst + kMpListCap * 8u;  // [0],[3] claim cursors (even / odd pass), [1] own-community weight, [2] overflow flag
+  for (int s = tid; s < CAP; s += TPB) sts64(tbl + s * 8u, kEmptyKeyU, 0u);
+  if (tid < 4) sts_u32(meta + tid * 4u, 0u);
+  __syncthreads();
+
+  for (int item = blockIdx.x; item < n; item += gridDim.x) {
+    const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(p.vrec + first + item));
+    const vid_t v = static_cast<vid_t>(r4.x);
+    const int deg = static_cast<int>(r4.z);
+    const uint2 me = __ldg(&p.packed[lm_self(p, r4.x, first + item)]);
+    const vid_t *__restrict__ row = p.tails + r4.y;
+    const uint32_t *__restrict__ wrow = p.weights + r4.y;
+    uint2 *__restrict__ srow = stage + __ldg(&stage_off[item]);
+    const double vd = u32_to_f64(r4.w);
+    const double ax = u32_to_f64(me.y) - vd;
+    int log2p = 1;
+    while ((kMpTarget << log2p) < deg) ++log2p;
+    bool staged = false;
+    double g, eix = 0.0, counter0 = 0.0;
+    uint32_t id;
+    bool redo;
+    do {
+      redo = false;
+      g = -1.0;
+      id = kLabelMask;
+      for (int pass = 0; pass < (1 << log2p); ++pass) {
+        uint32_t own = 0u;
+        for (int base = wib * 32; base < deg; base += TPB * UB) {
+          uint2 pk[UB];
+          uint32_t w[UB];
+          bool valid[UB];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int idx = base + u * TPB + static_cast<int>(lane);
+            valid[u] = idx < deg;
+            w[u] = 1u;
+            pk[u] = me;
+            if (valid[u]) {
+              if (!UNIT) w[u] = __ldg(wrow + idx);
+              if (staged) pk[u] = __ldcg(srow + idx);
+            }
+          }
+          if (!staged) {
+            uint32_t t[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u)
+              if (valid[u]) t[u] = static_cast<uint32_t>(__ldcs(row + base + u * TPB + static_cast<int>(lane)));
+#pragma unroll
+            for (int u = 0; u < UB; ++u)
+              if (valid[u]) pk[u] = __ldg(&p.packed[t[u]]);
+#pragma unroll
+            for (int u = 0; u < UB; ++u)
+              if (valid[u]) __stcg(srow + base + u * TPB + static_cast<int>(lane), pk[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const uint32_t key = pk[u].x;
+            const bool mine = valid[u] && key != me.x && static_cast<int>((key * 0xC2B2AE35u) >> (32 - log2p)) == pass;
+            if (valid[u] && key == me.x && pass == 0) own += w[u];
+            uint32_t so = 0u;
+            bool fresh = false;
+            if (mine) {
+              uint32_t s2 = lm_home<kMpCapLog2>(key);
+              const uint32_t step = (((key * 0x85EBCA6Bu) >> (29 - kMpCapLog2)) & kMaskB) | 8u;
+              uint32_t o2 = atoms_cas(tbl + s2, kEmptyKeyU, key);
+              while (o2 != kEmptyKeyU && o2 != key) {
+                s2 = (s2 + step) & kMaskB;
+                o2 = atoms_cas(tbl + s2, kEmptyKeyU, key);
+              }
+              so = tbl + s2;
+              fresh = o2 == kEmptyKeyU;
+              if (!UNIT || !fresh) reds_add(so + 4u, w[u]);  // unit weights: the slot counts later entries only
+            }
+            __syncwarp();
+            const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+            if (fm) {
+              uint32_t pos = 0u;
+              if (lane == static_cast<unsigned>(__ffs(fm) - 1))
+                pos = atomicAdd(reinterpret_cast<uint32_t *>(lm_smem + kTblBytes + kMpListCap * 8u + ((pass & 1) ? 12u : 0u)), __popc(fm));
+              pos = __shfl_sync(0xffffffffu, pos, __ffs(fm) - 1) + __popc(fm & ((1u << lane) - 1u));
+              if (fresh) {
+                if (pos < kMpListCap) sts64(lst + pos * 8u, so, pk[u].y);
+                else sts_u32(meta + 8u, 1u);  // overflow: redo with more passes
+              }
+            }
+          }
+        }
+        if (pass == 0) {
+          own = __reduce_add_sync(0xffffffffu, own);
+          if (lane == 0 && own) atomicAdd(reinterpret_cast<uint32_t *>(lm_smem + kTblBytes + kMpListCap * 8u + 4u), own);
+        }
+        __syncthreads();  // the pass is in the table
+        staged = true;
+        if (pass == 0) {
+          counter0 = u32_to_f64(lds_u32(meta + 4u));
+          eix = counter0;
+          if (p.selfw != nullptr) eix = counter0 - u32_to_f64(__ldg(&p.selfw[v]));
+        }
+        const bool over = lds_u32(meta + 8u) != 0u;
+        uint32_t cnt = lds_u32(meta + ((pass & 1) ? 12u : 0u));
+        if (tid == 0) sts_u32(meta + ((pass & 1) ? 0u : 12u), 0u);  // the other cursor: free since the last barrier but one
+        cnt = cnt > static_cast<uint32_t>(kMpListCap) ? static_cast<uint32_t>(kMpListCap) : cnt;
+        for (uint32_t j = tid; j < cnt; j += TPB) {
+          const uint2 rec = lds64(lst + j * 8u);
+          const uint2 kw = lds64(rec.x);
+          sts64(rec.x, kEmptyKeyU, 0u);
+          const uint32_t tot = UNIT ? kw.y + 1u : kw.y;
+          const double g2 = modularity_gain(u32_to_f64(tot), eix, vd, u32_to_f64(rec.y), ax, p.constant);
+          if (lm_better(g2, kw.x, g, id)) {
+            g = g2;
+            id = kw.x;
+          }
+        }
+        __syncthreads();  // every claimed slot is free again
+        if (over) {  // block-uniform: a claim did not fit the list — its slot was never freed
+          for (int s = tid; s < CAP; s += TPB) sts64(tbl + s * 8u, kEmptyKeyU, 0u);
+          if (tid == 0) {
+            sts_u32(meta, 0u);
+            sts_u32(meta + 4u, 0u);
+            sts_u32(meta + 8u, 0u);
+            sts_u32(meta + 12u, 0u);
+            if (redo_count) atomicAdd(redo_count, 1);
+          }
+          ++log2p;
+          redo = true;
+          __syncthreads();
+          break;
+        }
+      }
+    } while (redo);
+    double wg;
+    uint32_t wid = warp_argmax(g, id, &wg);
+    if (lane == 0) {
+      red_g[wib] = wg;
+      red_id[wib] = wid;
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 1; i < 32; ++i)
+        if (lm_better(red_g[i], red_id[i], wg, wid)) {
+          wg = red_g[i];
+          wid = red_id[i];
+        }
+      lm_commit(p, v, me.x, wg, wid, vd, counter0);
+      sts_u32(meta, 0u);
+      sts_u32(meta + 4u, 0u);
+      sts_u32(meta + 12u, 0u);
+    }
+    __syncthreads();
+  }
+}
+
+// stage_off[i] = first staging slot of the i-th vertex of the multi-pass classes (exclusive sum of degrees)
+__global__ void k_mp_degrees(const VertexRec *__restrict__ vrec, int n, uint32_t *__restrict__ deg) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) deg[i] = vrec[i].deg;
+}
+
+// ---------------------------------------------------------------------------
+// First sweep of a phase on graphs whose rows hold each tail at most once:
+// every vertex is its own community, so all neighbour communities are
+// distinct — no table.  The community of entry e is its tail's id, read with
+// its degree from packed[] (one gather), eix = 0 and counter[0] is the self-loop.
+// ---------------------------------------------------------------------------
+template <int U, int STRIDE, bool UNIT>
+__device__ __forceinline__ void lm_first_entries(const LmParams &p, const vid_t *__restrict__ row,
+                                                 const uint32_t *__restrict__ wrow, uint32_t self, double vd, double ax,
+                                                 double &g, uint32_t &id) {
+  uint32_t tail[U], w[U];
+  uint2 pk[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    tail[u] = static_cast<uint32_t>(__ldcs(row + u * STRIDE));
+    w[u] = UNIT ? 1u : __ldcs(wrow + u * STRIDE);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) pk[u] = __ldg(&p.packed[tail[u]]);  // {id | singleton bit, vertex degree}
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const double g2 = modularity_gain(u32_to_f64(w[u]), 0.0, vd, u32_to_f64(pk[u].y), ax, p.constant);
+    // a self-loop entry is the vertex's own community, never a candidate
+    if (tail[u] != self && lm_better(g2, pk[u].x, g, id)) {
+      g = g2;
+      id = pk[u].x;
+    }
+  }
+}
+
+template <int STRIDE, bool UNIT>
+__device__ __forceinline__ void lm_first_row(const LmParams &p, const vid_t *__restrict__ row,
+                                             const uint32_t *__restrict__ wrow, int lane_pos, int deg, uint32_t self,
+                                             double vd, double ax, double &g, uint32_t &id) {
+  int i = lane_pos;
+  for (; i + 3 * STRIDE < deg; i += 4 * STRIDE)
+    lm_first_entries<4, STRIDE, UNIT>(p, row + i, wrow + i, self, vd, ax, g, id);
+  if (i + STRIDE < deg) {
+    lm_first_entries<2, STRIDE, UNIT>(p, row + i, wrow + i, self, vd, ax, g, id);
+    i += 2 * STRIDE;
+  }
+  if (i < deg) lm_first_entries<1, STRIDE, UNIT>(p, row + i, wrow + i, self, vd, ax, g, id);
+}
+
+template <int G, bool UNIT>
+__global__ void __launch_bounds__(256) k_lm_first_group(LmParams p, int first, int n) {
+  constexpr int NG = 32 / G;
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = static_cast<int>(threadIdx.x >> 5);
+  const int grp = static_cast<int>(lane) / G, lig = static_cast<int>(lane) % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~static_cast<unsigned>(G - 1)));
+  const int nbatch = (n + NG - 1) / NG;
+  for (int b = blockIdx.x * 8 + wib; b < nbatch; b += gridDim.x * 8) {
+    const int item = b * NG + grp;
+    const bool live = item < n;
+    const uint4 r4 = live ? __ldg(reinterpret_cast<const uint4 *>(p.vrec + first + item)) : make_uint4(0u, 0u, 0u, 0u);
+    const vid_t v = static_cast<vid_t>(r4.x);
+    const int deg = static_cast<int>(r4.z);
+    const uint32_t self = live ? lm_self(p, r4.x, first + item) : 0u;
+    const uint2 me = __ldg(&p.packed[self]);
+    const double vd = u32_to_f64(r4.w);
+    const double ax = u32_to_f64(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+    lm_first_row<G, UNIT>(p, p.tails + r4.y, p.weights + r4.y, lig, deg, self, vd, ax, g, id);
+    double wg;
+    const uint32_t wid = lm_group_argmax<G>(g, id, &wg);
+    if (live && lig == 0) {
+      const double counter0 = (p.selfw != nullptr) ? u32_to_f64(__ldg(&p.selfw[v])) : 0.0;
+      lm_commit(p, v, me.x, wg, wid, vd, counter0);
+    }
+  }
+}
+
+template <int TPV, bool UNIT>
+__global__ void __launch_bounds__(TPV) k_lm_first_block(LmParams p, int first, int n) {
+  constexpr int kWarps = TPV / 32;
+  __shared__ double red_g[kWarps];
+  __shared__ uint32_t red_id[kWarps];
+  const int tid = static_cast<int>(threadIdx.x);
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = tid >> 5;
+  for (int item = blockIdx.x; item < n; item += gridDim.x) {
+    const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(p.vrec + first + item));
+    const vid_t v = static_cast<vid_t>(r4.x);
+    const int deg = static_cast<int>(r4.z);
+    const uint32_t self = lm_self(p, r4.x, first + item);
+    const uint2 me = __ldg(&p.packed[self]);
+    const double vd = u32_to_f64(r4.w);
+    const double ax = u32_to_f64(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+    lm_first_row<TPV, UNIT>(p, p.tails + r4.y, p.weights + r4.y, tid, deg, self, vd, ax, g, id);
+    double wg;
+    uint32_t wid = warp_argmax(g, id, &wg);
+    if (lane == 0) {
+      red_g[wib] = wg;
+      red_id[wib] = wid;
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 1; i < kWarps; ++i)
+        if (lm_better(red_g[i], red_id[i], wg, wid)) {
+          wg = red_g[i];
+          wid = red_id[i];
+        }
+      const double counter0 = (p.selfw != nullptr) ? u32_to_f64(__ldg(&p.selfw[v])) : 0.0;
+      lm_commit(p, v, me.x, wg, wid, vd, counter0);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace cvb

@@ -46,7 +46,15 @@ struct SweepU32Params {
   const vid_t *__restrict__ labels;      // [nv_global] the labels every sweep reads
   const uint32_t *__restrict__ cdeg32;   // [nv_global] (uint32) cdeg
   const int32_t *__restrict__ csize;     // [nv_global]
+  // degree-ordered gather layout (lm.cuh): packed[] is indexed by rank[global id] and `tails` holds ranks
+  const vid_t *__restrict__ rank;        // [nv_global] or nullptr (identity)
 };
+
+// index of local vertex v's own record in packed[] (and the value its self-loop entries carry in tails[])
+__device__ __forceinline__ vid_t self_of(const SweepU32Params &p, vid_t v) {
+  const vid_t g = v + p.base;
+  return p.rank != nullptr ? p.rank[g] : g;
+}
 
 __global__ void k_cdeg32(int64_t nv_global, const double *__restrict__ cdeg, uint32_t *__restrict__ cdeg32) {
   for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < nv_global;
@@ -55,13 +63,15 @@ __global__ void k_cdeg32(int64_t nv_global, const double *__restrict__ cdeg, uin
 }
 
 // packed[v] = {labels[v] | (csize[labels[v]] == 1) << 31, (uint32) cdeg[labels[v]]}
+// rank (optional): the record of vertex v is written at packed[rank[v]] (degree-ordered gather layout, lm.cuh)
 __global__ void k_pack_labels(int64_t nv_global, const vid_t *__restrict__ labels, const double *__restrict__ cdeg,
-                              const int32_t *__restrict__ csize, uint2 *__restrict__ packed) {
+                              const int32_t *__restrict__ csize, uint2 *__restrict__ packed,
+                              const vid_t *__restrict__ rank = nullptr) {
   for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < nv_global;
        v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const vid_t l = labels[v];
     const uint32_t flag = (csize[l] == 1) ? kSingletonBit : 0u;
-    packed[v] = make_uint2(static_cast<uint32_t>(l) | flag, static_cast<uint32_t>(cdeg[l]));
+    packed[rank != nullptr ? rank[v] : v] = make_uint2(static_cast<uint32_t>(l) | flag, static_cast<uint32_t>(cdeg[l]));
   }
 }
 
@@ -99,7 +109,7 @@ __global__ void __launch_bounds__(256) k_sweep_u32_t4(SweepU32Params p, const vi
   const vid_t v = list[i];
   const eid_t e0 = p.offsets[v];
   const int deg = static_cast<int>(p.offsets[v + 1] - e0);
-  const vid_t self = v + p.base;
+  const vid_t self = self_of(p, v);
   const uint2 me = p.packed[self];
   const uint32_t cc = me.x & kLabelMask;
   const double vd = p.vdeg[v];
@@ -132,15 +142,15 @@ __global__ void __launch_bounds__(256) k_sweep_u32_t4(SweepU32Params p, const vi
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     if (key[j] != kEmptyKeyU && (key[j] & kLabelMask) == cc) c0 = w[j];
-  const double counter0 = static_cast<double>(c0);
-  const double eix = counter0 - static_cast<double>(selfloop);
-  const double ax = static_cast<double>(me.y) - vd;
+  const double counter0 = u32_to_f64(c0);
+  const double eix = counter0 - u32_to_f64(selfloop);
+  const double ax = u32_to_f64(me.y) - vd;
   double g = -1.0;
   uint32_t id = kLabelMask;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     if (key[j] != kEmptyKeyU && (key[j] & kLabelMask) != cc) {
-      const double g2 = modularity_gain(static_cast<double>(w[j]), eix, vd, static_cast<double>(ay[j]), ax, p.constant);
+      const double g2 = modularity_gain(u32_to_f64(w[j]), eix, vd, u32_to_f64(ay[j]), ax, p.constant);
       if (better_u(g2, key[j], g, id)) {
         g = g2;
         id = key[j];
@@ -162,7 +172,7 @@ __global__ void __launch_bounds__(256) k_sweep_u32_group(SweepU32Params p, const
   const vid_t v = list[gid];
   const eid_t e0 = p.offsets[v];
   const int deg = static_cast<int>(p.offsets[v + 1] - e0);
-  const vid_t self = v + p.base;
+  const vid_t self = self_of(p, v);
   const uint2 me = p.packed[self];
   const uint32_t cc = me.x & kLabelMask;
   const bool valid = lig < deg;
@@ -181,20 +191,20 @@ __global__ void __launch_bounds__(256) k_sweep_u32_group(SweepU32Params p, const
   const uint32_t s = group_sum_ordered<uint32_t>(gmask, m, w, 0u, lane);
   const unsigned ccb = __ballot_sync(gmask, leader && (key & kLabelMask) == cc);
   const uint32_t c0 = __shfl_sync(gmask, s, ccb ? (__ffs(ccb) - 1) : static_cast<int>(lane));
-  const double counter0 = ccb ? static_cast<double>(c0) : 0.0;
+  const double counter0 = ccb ? u32_to_f64(c0) : 0.0;
   unsigned slb = __ballot_sync(gmask, valid && tail == self);
   double selfloop = 0.0;
   while (slb) {
-    selfloop += static_cast<double>(__shfl_sync(gmask, w, __ffs(slb) - 1));
+    selfloop += u32_to_f64(__shfl_sync(gmask, w, __ffs(slb) - 1));
     slb &= slb - 1u;
   }
   const double vd = p.vdeg[v];
   const double eix = counter0 - selfloop;
-  const double ax = static_cast<double>(me.y) - vd;
+  const double ax = u32_to_f64(me.y) - vd;
   double g = -1.0;
   uint32_t id = kLabelMask;
   if (leader && (key & kLabelMask) != cc) {
-    g = modularity_gain(static_cast<double>(s), eix, vd, static_cast<double>(ay), ax, p.constant);
+    g = modularity_gain(u32_to_f64(s), eix, vd, u32_to_f64(ay), ax, p.constant);
     id = key;
   }
 #pragma unroll
@@ -420,7 +430,7 @@ __device__ __forceinline__ VertexHeader fetch_header(const SweepU32Params &p, vi
   h.v = v;
   h.e0 = p.offsets[v];
   h.e1 = p.offsets[v + 1];
-  h.me = p.packed[v + p.base];
+  h.me = p.packed[self_of(p, v)];
   h.vd = p.vdeg[v];
   return h;
 }
@@ -511,7 +521,7 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
     const vid_t v = hc.v;
     const eid_t e0 = hc.e0, e1 = hc.e1;
     const int deg = static_cast<int>(e1 - e0);
-    const vid_t self = v + p.base;
+    const vid_t self = self_of(p, v);
     const uint2 me = hc.me;
     const uint32_t cc = me.x & kLabelMask;
     const double vd = hc.vd;
@@ -601,9 +611,9 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
     }
 
     // ---- evaluate: the claimer of each key reads its total and frees the slot ----
-    const double counter0 = static_cast<double>(c0u);
-    const double eix = counter0 - static_cast<double>(slu);
-    const double ax = static_cast<double>(me.y) - vd;
+    const double counter0 = u32_to_f64(c0u);
+    const double eix = counter0 - u32_to_f64(slu);
+    const double ax = u32_to_f64(me.y) - vd;
     double g = -1.0;
     uint32_t id = kLabelMask;
     if (SPLIT) {  // community degrees of this lane's claims: all gathers in flight before the first use
@@ -617,7 +627,7 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
         const uint32_t tot = lds_u32(a + capb);
         sts_u32(a, kEmptyKeyU);
         sts_u32(a + capb, 0u);
-        const double g2 = modularity_gain(static_cast<double>(tot), eix, vd, static_cast<double>(cay[q]), ax, p.constant);
+        const double g2 = modularity_gain(u32_to_f64(tot), eix, vd, u32_to_f64(cay[q]), ax, p.constant);
         if (better_u(g2, ckey[q], g, id)) {
           g = g2;
           id = ckey[q];
@@ -738,7 +748,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_u32_cluster(SweepU32Params p,
     const vid_t v = list[item];
     const eid_t e0 = p.offsets[v], e1 = p.offsets[v + 1];
     const int deg = static_cast<int>(e1 - e0);
-    const vid_t self = v + p.base;
+    const vid_t self = self_of(p, v);
     const uint2 me = p.packed[self];
     const uint32_t cc = me.x & kLabelMask;
     const double vd = p.vdeg[v];
@@ -829,9 +839,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_u32_cluster(SweepU32Params p,
     }
     cluster_sync_all();  // every insert of every CTA has landed
 
-    const double counter0 = static_cast<double>(ldc_u32(maddr0 + 8));
-    const double eix = counter0 - static_cast<double>(ldc_u32(maddr0 + 4));
-    const double ax = static_cast<double>(me.y) - vd;
+    const double counter0 = u32_to_f64(ldc_u32(maddr0 + 8));
+    const double eix = counter0 - u32_to_f64(ldc_u32(maddr0 + 4));
+    const double ax = u32_to_f64(me.y) - vd;
     double g = -1.0;
     uint32_t id = kLabelMask;
 #pragma unroll
@@ -840,7 +850,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_u32_cluster(SweepU32Params p,
         const uint32_t tot = ldc_u32(caddr[q] + capb);
         stc_u32(caddr[q], kEmptyKeyU);
         stc_u32(caddr[q] + capb, 0u);
-        const double g2 = modularity_gain(static_cast<double>(tot), eix, vd, static_cast<double>(cay[q]), ax, p.constant);
+        const double g2 = modularity_gain(u32_to_f64(tot), eix, vd, u32_to_f64(cay[q]), ax, p.constant);
         if (better_u(g2, ckey[q], g, id)) {
           g = g2;
           id = ckey[q];
@@ -918,11 +928,11 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_u32_twopass(SweepU32Params p,
     const vid_t v = list[item];
     const eid_t e0 = p.offsets[v];
     const int deg = static_cast<int>(p.offsets[v + 1] - e0);
-    const vid_t self = v + p.base;
+    const vid_t self = self_of(p, v);
     const uint2 me = p.packed[self];
     const uint32_t cc = me.x & kLabelMask;
     const double vd = p.vdeg[v];
-    const double ax = static_cast<double>(me.y) - vd;
+    const double ax = u32_to_f64(me.y) - vd;
     const vid_t *__restrict__ row_tails = p.tails + e0;
     const uint32_t *__restrict__ row_weights = p.weights + e0;
     double g = -1.0, eix = 0.0, counter0 = 0.0;
@@ -968,8 +978,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_u32_twopass(SweepU32Params p,
       }
       __syncthreads();
       if (half == 0u) {
-        counter0 = static_cast<double>(meta[2]);
-        eix = counter0 - static_cast<double>(meta[1]);
+        counter0 = u32_to_f64(meta[2]);
+        eix = counter0 - u32_to_f64(meta[1]);
       }
       // evaluate and free this half's table: 16 slots per thread, 4 records in flight
 #pragma unroll
@@ -995,7 +1005,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_u32_twopass(SweepU32Params p,
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (rk[j] != kEmptyKeyU) {
-            const double g2 = modularity_gain(static_cast<double>(rw[j]), eix, vd, ayv[j], ax, p.constant);
+            const double g2 = modularity_gain(u32_to_f64(rw[j]), eix, vd, ayv[j], ax, p.constant);
             if (better_u(g2, rk[j], g, id)) {
               g = g2;
               id = rk[j];
@@ -1173,7 +1183,7 @@ __global__ void __launch_bounds__(512, 2) k_sweep_u32_giant_insert(SweepU32Param
     const eid_t ve0 = p.offsets[v], ve1 = p.offsets[v + 1];
     const eid_t e0 = ve0 + (chunk - gt.chunk_start[gi]) * kGiantChunk;
     const eid_t e1 = (e0 + kGiantChunk < ve1) ? e0 + kGiantChunk : ve1;
-    const vid_t self = v + p.base;
+    const vid_t self = self_of(p, v);
     const uint32_t cc = p.packed[self].x & kLabelMask;
     const int64_t tbase = gt.table_start[gi];
     const int64_t gcap = gt.table_start[gi + 1] - tbase;
@@ -1290,12 +1300,12 @@ __global__ void __launch_bounds__(512) k_sweep_u32_giant_eval_dense(SweepU32Para
     uint32_t id = kLabelMask;
     if (off < cnt) {  // block-uniform
       const vid_t v = list[gi];
-      const uint2 me = p.packed[v + p.base];
+      const uint2 me = p.packed[self_of(p, v)];
       const double vd = p.vdeg[v];
       const uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
-      const double counter0 = static_cast<double>(__ldcg(&meta[2]));
-      const double eix = counter0 - static_cast<double>(__ldcg(&meta[1]));
-      const double ax = static_cast<double>(me.y) - vd;
+      const double counter0 = u32_to_f64(__ldcg(&meta[2]));
+      const double eix = counter0 - u32_to_f64(__ldcg(&meta[1]));
+      const double ax = u32_to_f64(me.y) - vd;
       uint32_t *__restrict__ dense = gt.dense + static_cast<int64_t>(gi - gt.vert_lo) * gt.dense_stride;
       const uint32_t *__restrict__ keys = gt.klist + first * kGiantChunk + off;
       const uint32_t m = (cnt - off < kGiantChunk) ? cnt - off : kGiantChunk;
@@ -1318,7 +1328,7 @@ __global__ void __launch_bounds__(512) k_sweep_u32_giant_eval_dense(SweepU32Para
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (rw[j]) {
-            const double g2 = modularity_gain(static_cast<double>(rw[j]), eix, vd, ayv[j], ax, p.constant);
+            const double g2 = modularity_gain(u32_to_f64(rw[j]), eix, vd, ayv[j], ax, p.constant);
             if (better_u(g2, rk[j], g, id)) {
               g = g2;
               id = rk[j];
@@ -1355,7 +1365,7 @@ __global__ void __launch_bounds__(128) k_sweep_u32_giant_final_dense(SweepU32Par
   const unsigned lane = threadIdx.x & 31u;
   if (gi >= n) return;
   const vid_t v = list[gi];
-  const uint2 me = p.packed[v + p.base];
+  const uint2 me = p.packed[self_of(p, v)];
   double g = -1.0;
   uint32_t id = kLabelMask;
   for (int64_t q = gt.chunk_start[gi] + lane; q < gt.chunk_start[gi + 1]; q += 32)
@@ -1367,7 +1377,7 @@ __global__ void __launch_bounds__(128) k_sweep_u32_giant_final_dense(SweepU32Par
   const uint32_t wid = warp_argmax(g, id, &wg);
   if (lane == 0) {
     uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
-    commit_vertex_u32(p, v, me.x, wg, wid, p.vdeg[v], static_cast<double>(meta[2]));
+    commit_vertex_u32(p, v, me.x, wg, wid, p.vdeg[v], u32_to_f64(meta[2]));
     meta[1] = 0u;
     meta[2] = 0u;
     gt.kcount[gi] = 0u;
@@ -1389,7 +1399,7 @@ __global__ void __launch_bounds__(512, 4) k_sweep_u32_giant_insert_direct(SweepU
     const eid_t ve0 = p.offsets[v], ve1 = p.offsets[v + 1];
     const eid_t e0 = ve0 + (chunk - gt.chunk_start[gi]) * kGiantChunk;
     const int cnt = static_cast<int>(((e0 + kGiantChunk < ve1) ? e0 + kGiantChunk : ve1) - e0);
-    const vid_t self = v + p.base;
+    const vid_t self = self_of(p, v);
     const uint32_t cc = p.packed[self].x & kLabelMask;
     const int64_t tbase = gt.table_start[gi];
     const int64_t gcap = gt.table_start[gi + 1] - tbase;
@@ -1444,12 +1454,12 @@ __global__ void __launch_bounds__(512) k_sweep_u32_giant_eval(SweepU32Params p, 
     const int gi = giant_owner(gt.table_start, n, s0);
     uint2 *__restrict__ tslots = gt.slots + (s0 - gt.slot_base);
     const vid_t v = list[gi];
-    const uint2 me = p.packed[v + p.base];
+    const uint2 me = p.packed[self_of(p, v)];
     const double vd = p.vdeg[v];
     const uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
-    const double counter0 = static_cast<double>(__ldcg(&meta[2]));
-    const double eix = counter0 - static_cast<double>(__ldcg(&meta[1]));
-    const double ax = static_cast<double>(me.y) - vd;
+    const double counter0 = u32_to_f64(__ldcg(&meta[2]));
+    const double eix = counter0 - u32_to_f64(__ldcg(&meta[1]));
+    const double ax = u32_to_f64(me.y) - vd;
     double g = -1.0;
     uint32_t id = kLabelMask;
 #pragma unroll
@@ -1469,7 +1479,7 @@ __global__ void __launch_bounds__(512) k_sweep_u32_giant_eval(SweepU32Params p, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (r[j].x != kEmptyKeyU) {
-          const double g2 = modularity_gain(static_cast<double>(r[j].y), eix, vd, ayv[j], ax, p.constant);
+          const double g2 = modularity_gain(u32_to_f64(r[j].y), eix, vd, ayv[j], ax, p.constant);
           if (better_u(g2, r[j].x, g, id)) {
             g = g2;
             id = r[j].x;
@@ -1503,7 +1513,7 @@ __global__ void __launch_bounds__(128) k_sweep_u32_giant_final(SweepU32Params p,
   const unsigned lane = threadIdx.x & 31u;
   if (gi >= n) return;
   const vid_t v = list[gi];
-  const uint2 me = p.packed[v + p.base];
+  const uint2 me = p.packed[self_of(p, v)];
   const int64_t p0 = gt.table_start[gi] / kGiantPiece, p1 = gt.table_start[gi + 1] / kGiantPiece;
   double g = -1.0;
   uint32_t id = kLabelMask;
@@ -1519,7 +1529,7 @@ __global__ void __launch_bounds__(128) k_sweep_u32_giant_final(SweepU32Params p,
   const uint32_t wid = warp_argmax(g, id, &wg);
   if (lane == 0) {
     uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
-    commit_vertex_u32(p, v, me.x, wg, wid, p.vdeg[v], static_cast<double>(meta[2]));
+    commit_vertex_u32(p, v, me.x, wg, wid, p.vdeg[v], u32_to_f64(meta[2]));
     meta[1] = 0u;
     meta[2] = 0u;
   }
@@ -1551,13 +1561,13 @@ __global__ void __launch_bounds__(256) k_sweep_u32_first(SweepU32Params p, const
     const bool live = item < n;
     const vid_t v = live ? list[item] : 0;
     const eid_t e0 = live ? p.offsets[v] : 0, e1 = live ? p.offsets[v + 1] : 0;
-    const vid_t self = v + p.base;
+    const vid_t self = self_of(p, v);
     const uint2 me = p.packed[self];
     const double vd = p.vdeg[v];
     // in the singleton state counter[0] == selfLoop, so eix = 0 for every gain;
     // the self-loop weight is only needed for clusterWeight and rides along
     const double eix = 0.0;
-    const double ax = static_cast<double>(me.y) - vd;
+    const double ax = u32_to_f64(me.y) - vd;
     double g = -1.0;
     uint32_t id = kLabelMask;
     uint32_t selfw = 0u;
@@ -1580,7 +1590,7 @@ __global__ void __launch_bounds__(256) k_sweep_u32_first(SweepU32Params p, const
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (t[k] != self) {
-          const double g2 = modularity_gain(static_cast<double>(w[k]), eix, vd, static_cast<double>(pk[k].y), ax, p.constant);
+          const double g2 = modularity_gain(u32_to_f64(w[k]), eix, vd, u32_to_f64(pk[k].y), ax, p.constant);
           if (better_u(g2, pk[k].x, g, id)) {
             g = g2;
             id = pk[k].x;
@@ -1601,7 +1611,7 @@ __global__ void __launch_bounds__(256) k_sweep_u32_first(SweepU32Params p, const
       slu = 0u;
       for (int i = 0; i < TPV / 32; ++i) slu += red_self[i];
     }
-    const double counter0 = static_cast<double>(slu);
+    const double counter0 = u32_to_f64(slu);
     if (TPV > 1) {
 #pragma unroll
       for (int o = GL / 2; o > 0; o >>= 1) {
@@ -1647,10 +1657,10 @@ __global__ void __launch_bounds__(512) k_sweep_u32_first_giant(SweepU32Params p,
     const eid_t ve0 = p.offsets[v], ve1 = p.offsets[v + 1];
     const eid_t e0 = ve0 + (chunk - gt.chunk_start[gi]) * kGiantChunk;
     const eid_t e1 = (e0 + kGiantChunk < ve1) ? e0 + kGiantChunk : ve1;
-    const vid_t self = v + p.base;
+    const vid_t self = self_of(p, v);
     const uint2 me = p.packed[self];
     const double vd = p.vdeg[v];
-    const double ax = static_cast<double>(me.y) - vd;
+    const double ax = u32_to_f64(me.y) - vd;
     double g = -1.0;
     uint32_t id = kLabelMask, selfw = 0u;
     vid_t t[8];
@@ -1671,7 +1681,7 @@ __global__ void __launch_bounds__(512) k_sweep_u32_first_giant(SweepU32Params p,
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (t[k] != self) {
-        const double g2 = modularity_gain(static_cast<double>(w[k]), 0.0, vd, static_cast<double>(pk[k].y), ax, p.constant);
+        const double g2 = modularity_gain(u32_to_f64(w[k]), 0.0, vd, u32_to_f64(pk[k].y), ax, p.constant);
         if (better_u(g2, pk[k].x, g, id)) {
           g = g2;
           id = pk[k].x;
@@ -1710,7 +1720,7 @@ __global__ void __launch_bounds__(128) k_sweep_u32_first_giant_final(SweepU32Par
   const unsigned lane = threadIdx.x & 31u;
   if (gi >= n) return;
   const vid_t v = list[gi];
-  const uint2 me = p.packed[v + p.base];
+  const uint2 me = p.packed[self_of(p, v)];
   double g = -1.0;
   uint32_t id = kLabelMask;
   for (int64_t q = gt.chunk_start[gi] + lane; q < gt.chunk_start[gi + 1]; q += 32)
@@ -1722,7 +1732,7 @@ __global__ void __launch_bounds__(128) k_sweep_u32_first_giant_final(SweepU32Par
   const uint32_t wid = warp_argmax(g, id, &wg);
   if (lane == 0) {
     uint32_t *meta = gt.gmeta + 3 * static_cast<int64_t>(gi);
-    commit_vertex_u32(p, v, me.x, wg, wid, p.vdeg[v], static_cast<double>(meta[1]));  // counter[0] = self-loop
+    commit_vertex_u32(p, v, me.x, wg, wid, p.vdeg[v], u32_to_f64(meta[1]));  // counter[0] = self-loop
     meta[1] = 0u;
   }
 }
