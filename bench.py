@@ -88,6 +88,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_name(scale, permuted):
+    """One name per workload, shared by both arms (the driver compares the strings)."""
+    return (f"R-MAT scale-{scale} ef16 (a,b,c,d=.57,.19,.19,.05) seed 2" + (", vertex ids permuted (seed 3)" if permuted else "")
+            + ", phase-0 local-move sweeps; metric = undirected edges per second per sweep")
+
+
 def make_graph(scale, device, permute):
     from cuvite_b200 import graphgen as gg
     return gg.rmat(scale, seed=2, device=device, permute_seed=3 if permute else None)
@@ -99,6 +105,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm is the CPU path on ALL host
+    # threads at every N (r01: the N>1 reference lines had silently run on one core)
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)
     import numpy as np
     from oracle.binding import Oracle, Reference
     import torch
@@ -113,6 +123,10 @@ def run_reference(args):
     else:
         impl, kind = Oracle(), "port"
         run = lambda: impl.phase(o, t, w)  # noqa: E731
+    try:
+        impl.set_num_threads(ncpu)
+    except Exception:
+        pass
     cores = impl.num_threads()
     warm = min(args.warmup, 1)
     for _ in range(warm):
@@ -128,7 +142,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * secs / iters, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"R-MAT scale-{scale} ef16 (a,b,c,d=.57,.19,.19,.05) seed 2, phase-0 sweeps",
+            "config": {"workload": workload_name(scale, args.gpus > 1),
                        "nv": g.nv, "csr_entries": g.ne, "sweeps_timed": iters,
                        "step": "one full phase-0 run of louvain.cpp (all its sweeps); ms_per_step is per sweep"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
@@ -136,6 +150,90 @@ def run_reference(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+GOLDEN_Q = os.path.join(ROOT, "tests", "golden", "bench_q.json")
+
+
+def golden_phase(scale, permuted):
+    """Phase-0 (Q, iterations) of a bench graph from the CPU checker (tools/make_bench_golden.py)."""
+    try:
+        return json.load(open(GOLDEN_Q)).get(f"rmat{scale}{'p' if permuted else ''}")
+    except Exception:
+        return None
+
+
+def device_steps(gpu, steps, warmup, ne, nv):
+    """W untimed + K timed device-resident steps on the graph `gpu` holds.  One step = one sweep +
+    community apply + modularity reduction; a converged phase restarts from singletons inside the
+    timed region.  The modularity of every iteration is kept: the first phase's trajectory is the
+    parity record of the run."""
+    import torch
+
+    def step(state):
+        gpu.sweep()
+        sums = gpu.apply_and_reduce()
+        q = gpu.modularity_from_sums(sums)
+        state["sweep_ms"].append(gpu.last_sweep_ms())
+        state["it"] += 1
+        state["iter_in_phase"].append(state["it"])
+        if state["phases"] == 0:
+            state["q_first_phase"].append(q)
+        if q - state["prev"] < 1e-6:  # phase converged: restart from singletons (inside the timed region)
+            if state["phases"] == 0:
+                state["phase_q"], state["phase_iters"] = max(state["prev"], -1.0), state["it"]
+            gpu.phase_reset()
+            state["prev"] = -1.0
+            state["phases"] += 1
+            state["it"] = 0
+        else:
+            state["prev"] = q
+            gpu.rotate_labels()
+
+    def fresh_state():
+        return {"prev": -1.0, "sweep_ms": [], "phases": 0, "it": 0, "iter_in_phase": [], "q_first_phase": [],
+                "phase_q": None, "phase_iters": None}
+
+    gpu.phase_begin()
+    st = fresh_state()
+    for _ in range(warmup):
+        step(st)
+    gpu.phase_reset()
+    st = fresh_state()
+    launches0 = gpu.launch_count
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(st)  # every step ends with a stream synchronise (the 2 sums reach the host)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    ms_per_step = wall_ms / steps  # host clock around synchronising steps == device-complete time
+    first_ms = [m for i, m in enumerate(st["sweep_ms"]) if st["iter_in_phase"][i] == 1]
+    later_ms = [m for i, m in enumerate(st["sweep_ms"]) if st["iter_in_phase"][i] > 1]
+    return {"state": st, "ms_per_step": ms_per_step, "value": (ne / 2) / (ms_per_step * 1e-3),
+            "sweep_ms": statistics.mean(st["sweep_ms"]), "launches": gpu.launch_count - launches0, "clocks": clocks,
+            "first_ms": first_ms, "later_ms": later_ms}
+
+
+def parity_record(scale, permuted, q_gpu, iters_gpu, cpu):
+    """GPU phase-0 result against the reference: the live cpu_baseline leg when it ran, and the
+    committed golden value of this graph.  Integer weights: every sum is exact, so the modularity
+    must be EQUAL, not close."""
+    rec = {"q_gpu": q_gpu, "iters_gpu": iters_gpu}
+    ok = q_gpu is not None
+    if cpu and cpu.get("q") is not None:
+        rec.update(q_reference_live=cpu["q"], iters_reference_live=cpu.get("iters"))
+        ok = ok and cpu["q"] == q_gpu and (cpu.get("iters") in (None, iters_gpu))
+    gold = golden_phase(scale, permuted)
+    if gold:
+        rec.update(q_golden=gold["q"], iters_golden=gold["iters"], golden_checker=gold["checker"])
+        ok = ok and gold["q"] == q_gpu and gold["iters"] == iters_gpu
+    rec["compared"] = bool((cpu and cpu.get("q") is not None) or gold)
+    rec["ok"] = bool(ok) if rec["compared"] else None
+    return rec
 
 
 # --------------------------------------------------------------------------- own arm, one GPU
@@ -155,55 +253,22 @@ def bench_single(args):
     info = gpu.info()
 
     # ---- device-resident steps ------------------------------------------------
-    def step(state):
-        gpu.sweep()
-        sums = gpu.apply_and_reduce()
-        q = gpu.modularity_from_sums(sums)
-        state["sweep_ms"].append(gpu.last_sweep_ms())
-        state["it"] += 1
-        state["iter_in_phase"].append(state["it"])
-        if q - state["prev"] < 1e-6:  # phase converged: restart from singletons (inside the timed region)
-            gpu.phase_reset()
-            state["prev"] = -1.0
-            state["phases"] += 1
-            state["it"] = 0
-        else:
-            state["prev"] = q
-            gpu.rotate_labels()
-
-    def fresh_state():
-        return {"prev": -1.0, "sweep_ms": [], "phases": 0, "it": 0, "iter_in_phase": []}
-
-    gpu.phase_begin()
-    st = fresh_state()
-    for _ in range(max(args.warmup, 3)):
-        step(st)
-    gpu.phase_reset()
-    st = fresh_state()
-    launches0 = gpu.launch_count
-    sampler = ClockSampler(0)
-    sampler.start()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step(st)  # every step ends with a stream synchronise (the 2 sums reach the host)
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop()
-    launches = gpu.launch_count - launches0
-    ms_per_step = wall_ms / args.steps  # host clock around synchronising steps == device-complete time
-    value = (ne / 2) / (ms_per_step * 1e-3)
-    sweep_ms = statistics.mean(st["sweep_ms"])
+    dev = device_steps(gpu, args.steps, max(args.warmup, 3), ne, nv)
+    st, ms_per_step, value, sweep_ms, launches, clocks = (dev["state"], dev["ms_per_step"], dev["value"],
+                                                          dev["sweep_ms"], dev["launches"], dev["clocks"])
     bytes_sweep = 12 * ne + 40 * nv
     peak, peak_src = measured_peak_gbs()
     achieved = bytes_sweep / (sweep_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if scale == BASE_SCALE and os.path.exists(tpath):  # ncu dram__bytes of the same command, committed
-        tj = json.load(open(tpath))
-        traffic, traffic_src = tj["mean_sweep_dram_bytes"], "profiles/r01_traffic.json (1 table-free + 3 hash sweeps)"
-    first_ms = [m for i, m in enumerate(st["sweep_ms"]) if st["iter_in_phase"][i] == 1]
-    later_ms = [m for i, m in enumerate(st["sweep_ms"]) if st["iter_in_phase"][i] > 1]
+    for tname in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if scale == BASE_SCALE and os.path.exists(tpath):  # ncu dram__bytes of the same command, committed
+            tj = json.load(open(tpath))
+            traffic = tj["mean_sweep_dram_bytes"]
+            traffic_src = (f"profiles/{tname}: a constant from a committed `ncu --set full` capture of this "
+                           "command (dram__bytes_read+write per sweep kernel group), not measured in this run")
+            break
+    first_ms, later_ms = dev["first_ms"], dev["later_ms"]
 
     # ---- end to end through the plugin call with pinned host buffers -----------
     o_h = g.offsets.cpu().numpy()
@@ -317,16 +382,45 @@ def bench_single(args):
             p = O.phase(o_h, t_cpu, w_cpu)
             kind, cores = "port", O.num_threads()
         cpu = {"value": (ne / 2) * p.iters / p.seconds, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": f"1 x phase 0 of the same graph ({p.iters} sweeps, {p.seconds:.2f} s)", "q": p.q}
+               "sample": f"1 x phase 0 of the same graph ({p.iters} sweeps, {p.seconds:.2f} s)", "q": p.q,
+               "iters": p.iters}
     except Exception as ex:  # the checker is optional for the number itself
         cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+
+    parity = parity_record(scale, False, st["phase_q"], st["phase_iters"], cpu)
+    parity["q_per_iteration_gpu"] = st["q_first_phase"]
+
+    # ---- the north-star configuration on ONE GPU: R-MAT scale-24, same steps, same timing ----------
+    scale24 = None
+    if args.scale is None and not args.no_scale24:
+        try:
+            del g
+            torch.cuda.empty_cache()
+            g24 = make_graph(24, "cuda", False)
+            gpu.upload_device(g24.offsets, g24.tails, g24.weights)
+            nv24, ne24 = g24.nv, g24.ne
+            del g24
+            torch.cuda.empty_cache()
+            d24 = device_steps(gpu, 8, 3, ne24, nv24)
+            b24 = 12 * ne24 + 40 * nv24
+            a24 = b24 / (d24["sweep_ms"] * 1e-3) / 1e9
+            p24 = parity_record(24, False, d24["state"]["phase_q"], d24["state"]["phase_iters"], None)
+            scale24 = {"workload": "R-MAT scale-24 ef16 seed 2 on one GPU (BASELINE.json north_star target config), "
+                                   "phase-0 sweeps, 8 timed steps after 3 warm-up steps",
+                       "nv": nv24, "csr_entries": ne24, "value": d24["value"], "unit": UNIT,
+                       "ms_per_step": d24["ms_per_step"], "sweep_kernels_ms": d24["sweep_ms"],
+                       "first_iteration_sweeps_ms": statistics.mean(d24["first_ms"]) if d24["first_ms"] else None,
+                       "later_iteration_sweeps_ms": statistics.mean(d24["later_ms"]) if d24["later_ms"] else None,
+                       "bound": "hbm", "achieved": a24, "peak": peak, "frac": a24 / peak, "traffic": None,
+                       "parity": p24, "clocks": d24["clocks"]}
+        except Exception as ex:  # reported, never fatal for the headline line
+            scale24 = {"error": repr(ex)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 weights / f64 gains" if info.weight_mode == 1 else "f64",
             "data": "synthetic",
-            "config": {"workload": f"R-MAT scale-{scale} ef16 (a,b,c,d=.57,.19,.19,.05) seed 2, phase-0 sweeps, "
-                                   "single local-move sweep per step", "nv": nv, "csr_entries": ne,
+            "config": {"workload": workload_name(scale, False), "nv": nv, "csr_entries": ne,
                        "undirected_edges": ne // 2, "parallelism": "1 GPU",
                        "l2": "inputs (8 B x entries = %d MB) larger than the 126 MB L2; no flush" % (8 * ne >> 20),
                        "sweep_kernels_ms": sweep_ms, "first_sweep_ms": st["sweep_ms"][0],
@@ -339,6 +433,8 @@ def bench_single(args):
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": "sweep kernel group (label pack + all degree-class kernels of one sweep), "
                                    "12E+40V algorithmic bytes, CUDA events on the engine stream"},
+            "roofline_scale24": scale24,
+            "parity": parity,
             "cpu_baseline": cpu,
             # e2e = the phase-level reference-facing call, distLouvainMethod(.., GpuGraph&) (louvain.hpp:93-97,
             # main.cpp:344) — the same boundary the reference arm (`--impl reference`: louvain.cpp's
@@ -353,6 +449,10 @@ def bench_single(args):
             "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)
     gpu.close()
+    bad = parity["ok"] is False or (isinstance(scale24, dict) and scale24.get("parity", {}).get("ok") is False)
+    if bad:
+        sys.stderr.write("bench.py: GPU modularity differs from the reference — see the parity record\n")
+        sys.exit(1)
 
 
 def main():
@@ -363,13 +463,14 @@ def main():
     ap.add_argument("--impl", default="cuvite_b200", choices=["cuvite_b200", "reference"])
     ap.add_argument("--scale", type=int, default=None, help="override the R-MAT scale (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (debug)")
+    ap.add_argument("--no-scale24", action="store_true", help="skip the roofline_scale24 block (debug)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         return bench_single(args)
     from cuvite_b200 import dist
-    return dist.bench_multi(args, METRIC, UNIT, BASE_SCALE, measured_peak_gbs, ClockSampler)
+    return dist.bench_multi(args, METRIC, UNIT, BASE_SCALE, measured_peak_gbs, ClockSampler, workload_name, parity_record)
 
 
 if __name__ == "__main__":

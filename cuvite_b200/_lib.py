@@ -66,6 +66,16 @@ SIGNATURES = {
     "cvb_graph_load_vite": (_i32, [_vp, C.c_char_p, _i32, _i32, _i32, C.POINTER(VitePart)]),
     "cvb_louvain_run": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "cvb_louvain_run_ex": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "cvb_dist_unique_id": (_i32, [_vp, _i32]),
+    "cvb_dist_init": (_i32, [_vp, _vp, _i32, _i32, _i32]),
+    "cvb_dist_finalize": (_i32, [_vp]),
+    "cvb_dist_set_parts": (_i32, [_vp, _vp]),
+    "cvb_dist_agree": (_i32, [_vp]),
+    "cvb_dist_phase_begin": (_i32, [_vp]),
+    "cvb_dist_sweep": (_i32, [_vp, C.POINTER(_f64)]),
+    "cvb_dist_advance": (_i32, [_vp]),
+    "cvb_dist_phase_run": (_i32, [_vp, _f64, _f64, _i32, C.POINTER(_f64), C.POINTER(_i32)]),
+    "cvb_dist_stage_ms": (_i32, [_vp, C.POINTER(_f64)]),
     "cvb_launch_count": (_i64, [_vp]),
     "cvb_last_sweep_ms": (C.c_float, [_vp]),
 }

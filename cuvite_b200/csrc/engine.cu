@@ -16,6 +16,7 @@
 #include "sweep_u32.cuh"
 #include "lm.cuh"
 #include "coarsen.cuh"
+#include "dist.cuh"
 
 namespace cvb {
 
@@ -219,6 +220,8 @@ struct cvb_engine {
   static constexpr int kAux = 4;
   cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr, nullptr};
+
+  DistState dist;  // N > 1: NCCL communicator and vertex ranges (dist.cuh)
 
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1103,6 +1106,77 @@ void cvb_destroy(cvb_engine *e) {
   delete e;
 }
 
+// Host-side narrowing of the boundary layout (the reference's 64-bit Edge{tail, weight}, 16 bytes per
+// entry) to what the device keeps — int32 tails, and uint32 weights only when some weight is not 1 — so
+// that the PCIe bill of an upload is 4 (or 8) bytes per entry instead of 16: r01's end-to-end number
+// was bound by exactly that copy.  Worker threads narrow fixed-size chunks into pinned staging while the
+// copies of the finished chunks are already in flight.  Returns 1 when the device arrays are filled and
+// e->mode is set, 0 when the graph needs the general path (a non-integer / negative / huge weight).
+static int upload_narrowed(cvb_engine *e, const void *edges_aos, const int64_t *tails, const double *weights,
+                           int64_t ne) {
+  static const int nt = [] {
+    if (const char *s = getenv("CVB_UPLOAD_THREADS")) return atoi(s) > 0 ? atoi(s) : 1;
+    const unsigned hw = std::thread::hardware_concurrency();
+    return static_cast<int>(hw >= 32 ? 16 : (hw >= 4 ? hw / 2 : 1));
+  }();
+  if (ne < (1 << 20) || getenv("CVB_NO_NARROW_UPLOAD")) return 0;
+  if (e->h_stage.ensure(static_cast<size_t>(ne) * 8 + 64) != CVB_OK) { cudaGetLastError(); return 0; }
+  if (e->tails.ensure(static_cast<size_t>(ne) + 1) != CVB_OK) return 0;
+  int32_t *ht = reinterpret_cast<int32_t *>(e->h_stage.p);
+  uint32_t *hw = reinterpret_cast<uint32_t *>(e->h_stage.p + static_cast<size_t>(ne) * 4);
+  const EdgeAoS *aos = static_cast<const EdgeAoS *>(edges_aos);
+  constexpr int64_t kChunk = int64_t(1) << 22;
+  struct Stat { int bad = 0, nonunit = 0; double sum = 0.0; };
+  std::vector<Stat> stat(nt);
+  for (int64_t c0 = 0; c0 < ne; c0 += kChunk) {
+    const int64_t c1 = c0 + kChunk < ne ? c0 + kChunk : ne;
+    std::vector<std::thread> th;
+    const int64_t per = (c1 - c0 + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+      const int64_t lo = c0 + t * per, hi = lo + per < c1 ? lo + per : c1;
+      if (lo >= hi) break;
+      th.emplace_back([=, &stat]() {
+        Stat s = stat[t];
+        for (int64_t i = lo; i < hi; ++i) {
+          const int64_t tl = aos ? aos[i].tail : tails[i];
+          const double w = aos ? aos[i].weight : weights[i];
+          if (!(w >= 0.0) || w >= 4294967296.0 || w != static_cast<double>(static_cast<uint32_t>(w)) || tl < 0 ||
+              tl > 2147483000LL)
+            s.bad = 1;
+          s.nonunit |= (w != 1.0);
+          s.sum += w;
+          ht[i] = static_cast<int32_t>(tl);
+          hw[i] = static_cast<uint32_t>(w);
+        }
+        stat[t] = s;
+      });
+    }
+    for (auto &x : th) x.join();
+    for (int t = 0; t < nt; ++t)
+      if (stat[t].bad) return 0;
+    if (cudaMemcpyAsync(e->tails.p + c0, ht + c0, (c1 - c0) * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream) !=
+        cudaSuccess)
+      return 0;
+  }
+  double sum = 0.0;
+  int nonunit = 0;
+  for (int t = 0; t < nt; ++t) {
+    sum += stat[t].sum;
+    nonunit |= stat[t].nonunit;
+  }
+  if (sum >= 4294967296.0) return 0;
+  if (e->weights.ensure((static_cast<size_t>(ne) + 1) * 4) != CVB_OK) return 0;
+  if (nonunit) {
+    if (cudaMemcpyAsync(e->weights.p, hw, ne * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream) != cudaSuccess)
+      return 0;
+  } else {
+    k_fill_u32<<<grid_for(ne, 256), 256, 0, e->stream>>>(reinterpret_cast<uint32_t *>(e->weights.p), ne, 1u);
+    e->launches++;
+  }
+  e->mode = CVB_WEIGHTS_U32;
+  return 1;
+}
+
 int cvb_graph_upload_host(cvb_engine *e, int64_t nv_local, int64_t base, int64_t nv_global,
                           const int64_t *offsets, const void *edges_aos, const int64_t *tails,
                           const double *weights) {
@@ -1117,6 +1191,15 @@ int cvb_graph_upload_host(cvb_engine *e, int64_t nv_local, int64_t base, int64_t
   CVB_TRY(e->offsets.ensure(nv_local + 2));
   CVB_CUDA(cudaMemcpyAsync(e->offsets.p, offsets, (nv_local + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
                            e->stream));
+  if (upload_narrowed(e, edges_aos, tails, weights, ne)) {
+    CVB_TRY(e->d_flags.ensure(4));
+    CVB_TRY(e->d_sums.ensure(4));
+    CVB_TRY(e->h_sums.ensure(64));
+    CVB_TRY(e->ticket.ensure(4));
+    CVB_TRY(e->partials.ensure(2 * 148 * 16 + 16));
+    CVB_CUDA(cudaMemsetAsync(e->ticket.p, 0, 4 * sizeof(unsigned int), e->stream));
+    return post_graph(e);
+  }
   CVB_TRY(e->staging.ensure(static_cast<size_t>(ne) * 16 + 16));
   if (edges_aos) {
     CVB_CUDA(cudaMemcpyAsync(e->staging.p, edges_aos, static_cast<size_t>(ne) * 16, cudaMemcpyHostToDevice,
@@ -1822,6 +1905,217 @@ int cvb_louvain_run_ex(cvb_engine *e, int max_levels, int flags, double *level_q
     if (err != cudaSuccess) { set_error("cvb_louvain_run: D2H failed: %s", cudaGetErrorString(err)); return CVB_ERR_CUDA; }
   }
   return phase;
+}
+
+// ---------------------------------------------------------------------------
+// N > 1 ranks: NCCL phase driver (dist.cuh).  Every function is collective: all
+// ranks call it in the same order.
+// ---------------------------------------------------------------------------
+int cvb_dist_unique_id(void *out, int nbytes) {
+  CVB_CHECK(out && nbytes >= static_cast<int>(sizeof(ncclUniqueId)), CVB_ERR_ARG, "cvb_dist_unique_id: need %d bytes",
+            static_cast<int>(sizeof(ncclUniqueId)));
+  NcclApi *n = nccl_api();
+  CVB_CHECK(n, CVB_ERR_STATE, "NCCL not available (dlopen libnccl.so.2 failed; set CVB_NCCL_LIB)");
+  ncclUniqueId id;
+  CVB_NCCL(n->GetUniqueId(&id));
+  memcpy(out, &id, sizeof id);
+  return CVB_OK;
+}
+
+int cvb_dist_init(cvb_engine *e, const void *id, int nbytes, int rank, int world) {
+  CVB_CHECK(e && world >= 1 && rank >= 0 && rank < world, CVB_ERR_ARG, "cvb_dist_init: bad rank/world");
+  DistState &d = e->dist;
+  d.rank = rank;
+  d.world = world;
+  d.timing = getenv("CVB_DIST_TIMING") && getenv("CVB_DIST_TIMING")[0] == '1';
+  if (d.timing && !d.ev[0])
+    for (auto &x : d.ev) CVB_CUDA(cudaEventCreate(&x));
+  if (world == 1) return CVB_OK;
+  CVB_CHECK(id && nbytes >= static_cast<int>(sizeof(ncclUniqueId)), CVB_ERR_ARG, "cvb_dist_init: missing unique id");
+  NcclApi *n = nccl_api();
+  CVB_CHECK(n, CVB_ERR_STATE, "NCCL not available (dlopen libnccl.so.2 failed; set CVB_NCCL_LIB)");
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof uid);
+  CVB_CUDA(cudaSetDevice(e->device));
+  CVB_NCCL(n->CommInitRank(&d.comm, world, uid, rank));
+  return CVB_OK;
+}
+
+int cvb_dist_finalize(cvb_engine *e) {
+  CVB_CHECK(e, CVB_ERR_ARG, "null engine");
+  if (e->dist.comm) {
+    cudaStreamSynchronize(e->stream);
+    nccl_api()->CommDestroy(e->dist.comm);
+    e->dist.comm = nullptr;
+  }
+  return CVB_OK;
+}
+
+int cvb_dist_set_parts(cvb_engine *e, const int64_t *parts) {
+  CVB_CHECK(e && e->graph_ready, CVB_ERR_STATE, "cvb_dist_set_parts: no graph uploaded");
+  DistState &d = e->dist;
+  d.parts.resize(d.world + 1);
+  for (int p = 0; p <= d.world; ++p)
+    d.parts[p] = parts ? parts[p] : (e->nvg * p) / d.world;  // distgraph.cpp:118-119
+  CVB_CHECK(d.parts[0] == 0 && d.parts[d.world] == e->nvg && d.parts[d.rank] == e->base &&
+                d.parts[d.rank + 1] == e->base + e->nvl,
+            CVB_ERR_ARG, "cvb_dist_set_parts: ranges do not match the uploaded rows [%lld, %lld)", (long long)e->base,
+            (long long)(e->base + e->nvl));
+  d.even = true;
+  for (int p = 0; p < d.world; ++p)
+    if (d.parts[p + 1] - d.parts[p] != d.parts[1] - d.parts[0]) d.even = false;
+  return CVB_OK;
+}
+
+namespace {
+// global[parts[p] .. parts[p+1]) <- rank p's local rows, for every p (device buffers, `elem` bytes per row)
+int dist_allgather_rows(cvb_engine *e, const void *local, void *global, int dtype, size_t elem) {
+  DistState &d = e->dist;
+  if (d.world == 1) {
+    if (local != global)
+      CVB_CUDA(cudaMemcpyAsync(static_cast<char *>(global) + e->base * elem, local, e->nvl * elem,
+                               cudaMemcpyDeviceToDevice, e->stream));
+    return CVB_OK;
+  }
+  NcclApi *n = nccl_api();
+  if (d.even) {
+    CVB_NCCL(n->AllGather(local, global, static_cast<size_t>(e->nvl), dtype, d.comm, e->stream));
+    return CVB_OK;
+  }
+  CVB_NCCL(n->GroupStart());  // uneven ranges (coarsened levels, -b): one broadcast per owner, fused in a group
+  for (int p = 0; p < d.world; ++p) {
+    const size_t cnt = static_cast<size_t>(d.parts[p + 1] - d.parts[p]);
+    if (cnt == 0) continue;
+    char *dst = static_cast<char *>(global) + d.parts[p] * elem;
+    n->Broadcast(p == d.rank ? local : dst, dst, cnt, dtype, p, d.comm, e->stream);
+  }
+  CVB_NCCL(n->GroupEnd());
+  return CVB_OK;
+}
+
+int dist_allreduce(cvb_engine *e, void *buf, size_t count, int dtype, int op) {
+  if (e->dist.world == 1) return CVB_OK;
+  CVB_NCCL(nccl_api()->AllReduce(buf, buf, count, dtype, op, e->dist.comm, e->stream));
+  return CVB_OK;
+}
+}  // namespace
+
+int cvb_dist_agree(cvb_engine *e) {
+  CVB_CHECK(e && e->graph_ready, CVB_ERR_STATE, "cvb_dist_agree: no graph uploaded");
+  DistState &d = e->dist;
+  if (d.parts.empty()) CVB_TRY(cvb_dist_set_parts(e, nullptr));
+  if (d.world == 1) return CVB_OK;
+  // the exact-integer mode is only valid when EVERY rank's weights are integers and the GLOBAL total
+  // stays below 2^32 (the replicated community degrees are global sums): agree on it
+  double h[2] = {e->mode == CVB_WEIGHTS_U32 ? 1.0 : 0.0, e->local_weight};
+  cudaStream_t st = e->stream;
+  CVB_CUDA(cudaMemcpyAsync(e->d_sums.p, h, sizeof h, cudaMemcpyHostToDevice, st));
+  CVB_TRY(dist_allreduce(e, e->d_sums.p, 1, ncclFloat64, ncclMin));
+  CVB_TRY(dist_allreduce(e, e->d_sums.p + 1, 1, ncclFloat64, ncclSum));
+  CVB_CUDA(cudaMemcpyAsync(h, e->d_sums.p, sizeof h, cudaMemcpyDeviceToHost, st));
+  CVB_CUDA(cudaStreamSynchronize(st));
+  const bool all_u32 = h[0] > 0.5 && h[1] < 4294967296.0;
+  if (!all_u32 && e->mode == CVB_WEIGHTS_U32) {
+    DevBuf<unsigned char> w2;
+    CVB_TRY(w2.ensure((static_cast<size_t>(e->ne) + 1) * 8));
+    if (e->ne > 0)
+      k_weights_u32_to_f64<<<grid_for(e->ne, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(e->weights.p),
+                                                                 reinterpret_cast<double *>(w2.p), e->ne);
+    CVB_CUDA(cudaStreamSynchronize(st));
+    std::swap(e->weights.p, w2.p);
+    std::swap(e->weights.cap, w2.cap);
+    w2.release();
+    e->mode = CVB_WEIGHTS_F64;
+    CVB_TRY(post_graph(e));
+  }
+  return CVB_OK;
+}
+
+int cvb_dist_phase_begin(cvb_engine *e) {
+  CVB_CHECK(e && e->graph_ready, CVB_ERR_STATE, "cvb_dist_phase_begin: no graph uploaded");
+  DistState &d = e->dist;
+  if (d.parts.empty() || d.parts[d.world] != e->nvg) CVB_TRY(cvb_dist_set_parts(e, nullptr));
+  cudaStream_t st = e->stream;
+  double tot = e->local_weight;  // distCalcConstantForSecondTerm's Allreduce, louvain.cpp:2175
+  if (d.world > 1) {
+    CVB_CUDA(cudaMemcpyAsync(e->d_sums.p, &tot, sizeof tot, cudaMemcpyHostToDevice, st));
+    CVB_TRY(dist_allreduce(e, e->d_sums.p, 1, ncclFloat64, ncclSum));
+    CVB_CUDA(cudaMemcpyAsync(&tot, e->d_sums.p, sizeof tot, cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(cudaStreamSynchronize(st));
+  }
+  d.total_weight = tot;
+  CVB_TRY(cvb_phase_begin(e, tot));
+  if (d.world > 1) {  // community degrees of every vertex: all-gather of the vertex degrees
+    CVB_TRY(dist_allgather_rows(e, e->vdeg.p, e->cdeg.p, ncclFloat64, sizeof(double)));
+    CVB_CUDA(cudaMemcpyAsync(e->vdeg_global.p, e->cdeg.p, e->nvg * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  d.stage_n = 0;
+  for (auto &x : d.stage_ms) x = 0.0;
+  return CVB_OK;
+}
+
+int cvb_dist_sweep(cvb_engine *e, double *q_out) {
+  CVB_CHECK(e && e->phase_ready && q_out, CVB_ERR_STATE, "cvb_dist_sweep: call cvb_dist_phase_begin first");
+  DistState &d = e->dist;
+  cudaStream_t st = e->stream;
+  double sums[2];
+  if (d.world == 1) {
+    CVB_TRY(cvb_sweep(e));
+    CVB_TRY(cvb_apply_and_reduce(e, sums));
+    *q_out = cvb_modularity_from_sums(e, sums);
+    return CVB_OK;
+  }
+  if (d.timing) CVB_CUDA(cudaEventRecord(d.ev[0], st));
+  CVB_TRY(cvb_sweep(e));
+  if (d.timing) CVB_CUDA(cudaEventRecord(d.ev[1], st));
+  // ghost labels: ONE all-gather of the new labels (replaces fillRemoteCommunities' label pull)
+  CVB_TRY(dist_allgather_rows(e, e->lab[e->targ].p, e->glabels_next(), ncclInt32, sizeof(vid_t)));
+  if (d.timing) CVB_CUDA(cudaEventRecord(d.ev[2], st));
+  // community info of ALL ranks' moves from the label diff, locally (replaces updateRemoteCommunities)
+  CVB_TRY(cvb_rebuild_and_reduce_async(e));
+  if (d.timing) CVB_CUDA(cudaEventRecord(d.ev[3], st));
+  CVB_TRY(dist_allreduce(e, e->d_sums.p, 2, ncclFloat64, ncclSum));  // louvain.cpp:2522
+  if (d.timing) CVB_CUDA(cudaEventRecord(d.ev[4], st));
+  CVB_CUDA(cudaMemcpyAsync(e->h_sums.p, e->d_sums.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (d.timing) CVB_CUDA(cudaEventRecord(d.ev[5], st));
+  CVB_CUDA(cudaStreamSynchronize(st));
+  memcpy(sums, e->h_sums.p, sizeof sums);
+  if (d.timing) {
+    for (int i = 0; i < 5; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, d.ev[i], d.ev[i + 1]);
+      d.stage_ms[i] += ms;
+    }
+    d.stage_n++;
+  }
+  *q_out = cvb_modularity_from_sums(e, sums);
+  return CVB_OK;
+}
+
+int cvb_dist_advance(cvb_engine *e) { return cvb_rotate_labels(e); }
+
+int cvb_dist_phase_run(cvb_engine *e, double lower, double thresh, int max_iters, double *q_out, int *iters_out) {
+  CVB_TRY(cvb_dist_phase_begin(e));
+  double prev = lower, cur = -1.0;
+  int iters = 0;
+  while (true) {  // louvain.cpp:638-739
+    iters++;
+    CVB_TRY(cvb_dist_sweep(e, &cur));
+    if ((cur - prev) < thresh) break;
+    prev = cur;
+    if (prev < lower) prev = lower;
+    if (max_iters > 0 && iters >= max_iters) break;
+    CVB_TRY(cvb_dist_advance(e));
+  }
+  if (q_out) *q_out = prev;
+  if (iters_out) *iters_out = iters;
+  return CVB_OK;
+}
+
+int cvb_dist_stage_ms(cvb_engine *e, double out[5]) {
+  CVB_CHECK(e && out, CVB_ERR_ARG, "null argument");
+  for (int i = 0; i < 5; ++i) out[i] = e->dist.stage_n ? e->dist.stage_ms[i] / e->dist.stage_n : 0.0;
+  return CVB_OK;
 }
 
 }  // extern "C"

@@ -59,6 +59,12 @@ __global__ void k_convert_edges(const void *__restrict__ aos, const int64_t *__r
   }
 }
 
+__global__ void k_fill_u32(uint32_t *__restrict__ dst, int64_t n, uint32_t v) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = v;
+}
+
 template <typename T64, typename T32>
 __global__ void k_narrow(const T64 *__restrict__ src, T32 *__restrict__ dst, int64_t n, int64_t add) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;

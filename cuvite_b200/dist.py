@@ -63,6 +63,21 @@ class DistLouvain:
         self.timing = [] if os.environ.get("CVB_DIST_TIMING") == "1" else None
         self._pinned = None
         self._set_nv_global(nv_global, parts)
+        # The real engine runs the phase natively (cvb_dist_*: NCCL issued from C++ on the engine
+        # stream); the stand-in engines of the CPU tests keep the torch.distributed path below, which
+        # is the same sequence of collectives.
+        self.native = bool(self.labels_only and world > 1 and hasattr(engine, "dist_init")
+                           and os.environ.get("CVB_DIST_NATIVE", "1") != "0")
+        if self.native:
+            uid = [engine.dist_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0, group=group)
+            engine.dist_init(uid[0], rank, world)
+            engine.dist_set_parts(self.parts)
+            engine.dist_agree()
+        elif world > 1 and hasattr(engine, "stream"):
+            # the collectives below run on torch's current stream; the engine must too
+            assert engine.stream == torch.cuda.current_stream().cuda_stream, \
+                "DistLouvain: create the engine on torch's current stream (GpuGraph(stream=...))"
 
     def _set_nv_global(self, nv_global: int, parts=None):
         self.nvg = nv_global
@@ -98,6 +113,10 @@ class DistLouvain:
     def phase_begin(self):
         """distInitLouvain across ranks: 2m by all-reduce, community degrees by all-gather."""
         e = self.e
+        if self.native:
+            e.dist_phase_begin()
+            self.constant = None
+            return
         info = e.info()
         self.dev = torch.device("cuda", torch.cuda.current_device()) if hasattr(e, "buffer") else torch.device("cpu")
         tot = torch.tensor([info.local_weight], dtype=torch.float64, device=self.dev)
@@ -119,6 +138,8 @@ class DistLouvain:
 
     def stage_times_ms(self):
         """Mean milliseconds per stage over the sweeps stamped so far (after a synchronize)."""
+        if self.native:
+            return self.e.dist_stage_ms()
         out, prev = {}, None
         for name, ev in self.timing or []:
             if name != "begin" and prev is not None:
@@ -129,6 +150,8 @@ class DistLouvain:
     def sweep(self):
         """One synchronous sweep + exchange.  Returns the modularity of this iteration."""
         e = self.e
+        if self.native:
+            return e.dist_sweep()
         self._mark("begin")
         e.sweep()
         self._mark("sweep_kernels")
@@ -222,6 +245,9 @@ class DistLouvain:
             keys, w = rkeys, rw
         e.graph_from_pairs(parts[self.rank + 1] - parts[self.rank], parts[self.rank], nc, keys, w)
         self._set_nv_global(nc)
+        if self.native:
+            e.dist_set_parts(self.parts)
+            e.dist_agree()
         return newid, nc
 
     @staticmethod
@@ -316,7 +342,7 @@ def load_partition(engine, g, rank: int, world: int, parts=None):
     return b0, b1, e1 - e0
 
 
-def bench_multi(args, metric, unit, base_scale, measured_peak_gbs, ClockSampler):
+def bench_multi(args, metric, unit, base_scale, measured_peak_gbs, ClockSampler, workload_name=None, parity_record=None):
     """bench.py at N > 1: weak scaling, R-MAT scale base+log2(N), hubs spread by a fixed permutation."""
     from . import build
     build.build()
@@ -340,20 +366,29 @@ def bench_multi(args, metric, unit, base_scale, measured_peak_gbs, ClockSampler)
     def step(state):
         q = dl.sweep()
         state["sweep_ms"].append(gpu.last_sweep_ms())
+        state["it"] += 1
+        if state["phases"] == 0:
+            state["qs"].append(q)
         if q - state["prev"] < 1e-6:
+            if state["phases"] == 0:
+                state["phase_q"], state["phase_iters"] = state["prev"], state["it"]
             dl.phase_begin()  # converged: restart from singletons inside the timed region
             state["prev"] = -1.0
             state["phases"] += 1
+            state["it"] = 0
         else:
             state["prev"] = q
             dl.advance()
 
+    def fresh():
+        return {"prev": -1.0, "sweep_ms": [], "phases": 0, "it": 0, "qs": [], "phase_q": None, "phase_iters": None}
+
     dl.phase_begin()
-    st = {"prev": -1.0, "sweep_ms": [], "phases": 0}
+    st = fresh()
     for _ in range(max(args.warmup, 3)):
         step(st)
     dl.phase_begin()
-    st = {"prev": -1.0, "sweep_ms": [], "phases": 0}
+    st = fresh()
     launches0 = gpu.launch_count
     if dl.timing is not None:
         dl.timing = []
@@ -388,11 +423,11 @@ def bench_multi(args, metric, unit, base_scale, measured_peak_gbs, ClockSampler)
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32 weights / f64 gains", "data": "synthetic",
-                "config": {"workload": f"R-MAT scale-{scale} ef16 (a,b,c,d=.57,.19,.19,.05) seed 2, vertex ids permuted "
-                                       "(seed 3), phase-0 sweeps, one sweep + label/delta exchange per step",
+                "config": {"workload": workload_name(scale, True),
                            "nv": nv, "csr_entries": ne, "undirected_edges": ne // 2,
-                           "parallelism": f"{world} GPUs, vertex-range partition parts[p]=nv*p//P, NCCL "
-                                          "allreduce(deltas)+allgather(labels)",
+                           "parallelism": f"{world} GPUs, vertex-range partition parts[p]=nv*p//P; per sweep: NCCL "
+                                          "allgather(labels) + local label-diff community rebuild + "
+                                          "allreduce(2 sums), issued from the C ABI (cvb_dist_sweep)",
                            "l2": "per-GPU inputs larger than L2; no flush",
                            "sweep_kernels_ms_max_rank": sweep_ms, "max_local_entries": int(ne_max.item()),
                            "phase_restarts_in_timed_region": st["phases"],
@@ -400,11 +435,16 @@ def bench_multi(args, metric, unit, base_scale, measured_peak_gbs, ClockSampler)
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                              "kernel": "sweep kernel group of the slowest rank, 12E+40V local bytes"},
+                "parity": ({**parity_record(scale, True, st["phase_q"], st["phase_iters"], None),
+                            "q_per_iteration_gpu": st["qs"]} if parity_record else None),
                 "cpu_baseline": None,
                 "e2e": {"value": None, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16,
                         "api": "device-resident distributed phase; see N=1 for the host-buffer plugin path"},
                 "gpu_launches": int(launches.item()), "clocks": clocks}
         print(json.dumps(line), flush=True)
+    bad = bool(parity_record and parity_record(scale, True, st["phase_q"], st["phase_iters"], None)["ok"] is False)
     gpu.close()
     dist.barrier()
     dist.destroy_process_group()
+    if bad:
+        raise SystemExit("bench.py: the N-GPU modularity differs from the reference — see the parity record")

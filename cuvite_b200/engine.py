@@ -157,6 +157,49 @@ class GpuGraph:
     def sync(self):
         check(self._L.cvb_sync(self._h), "sync")
 
+    # ---- N > 1 ranks: the phase over NCCL, behind the C ABI (cvb_dist_*) --------
+    @staticmethod
+    def dist_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(_lib.load().cvb_dist_unique_id(buf, 128), "dist_unique_id")
+        return buf.raw
+
+    def dist_init(self, uid: bytes | None, rank: int, world: int):
+        b = C.create_string_buffer(uid, 128) if uid is not None else None
+        check(self._L.cvb_dist_init(self._h, b, 128 if uid is not None else 0, rank, world), "dist_init")
+
+    def dist_set_parts(self, parts=None):
+        a = None if parts is None else np.ascontiguousarray(np.asarray(parts, dtype=np.int64))
+        check(self._L.cvb_dist_set_parts(self._h, None if a is None else _ptr(a)), "dist_set_parts")
+
+    def dist_agree(self):
+        check(self._L.cvb_dist_agree(self._h), "dist_agree")
+
+    def dist_phase_begin(self):
+        check(self._L.cvb_dist_phase_begin(self._h), "dist_phase_begin")
+
+    def dist_sweep(self) -> float:
+        q = C.c_double(0)
+        check(self._L.cvb_dist_sweep(self._h, C.byref(q)), "dist_sweep")
+        return q.value
+
+    def dist_advance(self):
+        check(self._L.cvb_dist_advance(self._h), "dist_advance")
+
+    def dist_phase_run(self, lower: float = -1.0, thresh: float = 1e-6, max_iters: int = 0):
+        q, it = C.c_double(0), C.c_int(0)
+        check(self._L.cvb_dist_phase_run(self._h, lower, thresh, max_iters, C.byref(q), C.byref(it)), "dist_phase_run")
+        return q.value, it.value
+
+    def dist_stage_ms(self):
+        out = (C.c_double * 5)()
+        check(self._L.cvb_dist_stage_ms(self._h, out), "dist_stage_ms")
+        return dict(zip(("sweep_kernels", "all_gather_labels", "label_diff_and_reduce", "all_reduce_sums", "read_back"),
+                        [float(x) for x in out]))
+
+    def dist_finalize(self):
+        check(self._L.cvb_dist_finalize(self._h), "dist_finalize")
+
     # ---- phase, whole ------------------------------------------------------
     def phase_run(self, lower: float = -1.0, thresh: float = 1e-6, max_iters: int = 0):
         q, it = C.c_double(0), C.c_int(0)

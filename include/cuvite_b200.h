@@ -294,6 +294,38 @@ int64_t cvb_launch_count(const cvb_engine *e);
  * stream; valid after a sync).  Returns < 0 when no sweep ran. */
 float cvb_last_sweep_ms(cvb_engine *e);
 
+/* ---- N > 1 ranks: the phase over NCCL ------------------------------------------------
+ * One engine per GPU / process holding the rows [parts[rank], parts[rank+1]) of the reference's
+ * vertex-range partition (distgraph.cpp:118-119, or the -b ranges).  These calls are collective
+ * (every rank, same order) and replace distLouvainMethod(..., GpuGraph&) at any rank count —
+ * louvain.hpp:93-97, louvain.cpp:591-753 — with its MPI ghost exchange: exchangeVertexReqs
+ * (3118-3264), fillRemoteCommunities (2588-2959), updateRemoteCommunities (2983-3116) and the
+ * Allreduces of louvain.cpp:2175 and 2522.  NCCL is resolved with dlopen at the first call.
+ *
+ * cvb_dist_unique_id : rank 0 makes the 128-byte NCCL id; the host program ships it to the other
+ *                      ranks by whatever it already has (MPI_Bcast, torch.distributed, a file).
+ * cvb_dist_init      : create the communicator on the engine's device.
+ * cvb_dist_set_parts : vertex ranges of the uploaded graph (parts[world+1]); NULL = nv*p/P.
+ * cvb_dist_agree     : after every upload: the exact-integer weight mode is kept only if ALL ranks
+ *                      have integer weights and the GLOBAL total stays below 2^32.
+ * cvb_dist_phase_begin / _sweep / _advance : distInitLouvain, one iteration (sweep + label
+ *                      all-gather + community rebuild + reduction; *q_out = this iteration's
+ *                      modularity, louvain.cpp:2472-2473), label rotation.
+ * cvb_dist_phase_run : the whole loop (same contract as cvb_phase_run).
+ * cvb_dist_stage_ms  : with CVB_DIST_TIMING=1, mean CUDA-event milliseconds of
+ *                      {sweep kernels, label all-gather, label diff + reduce, sums all-reduce, read-back}. */
+int cvb_dist_unique_id(void *out, int nbytes);
+int cvb_dist_init(cvb_engine *e, const void *id, int nbytes, int rank, int world);
+int cvb_dist_finalize(cvb_engine *e);
+int cvb_dist_set_parts(cvb_engine *e, const int64_t *parts);
+int cvb_dist_agree(cvb_engine *e);
+int cvb_dist_phase_begin(cvb_engine *e);
+int cvb_dist_sweep(cvb_engine *e, double *q_out);
+int cvb_dist_advance(cvb_engine *e);
+int cvb_dist_phase_run(cvb_engine *e, double lower, double thresh, int max_iters,
+                       double *q_out, int *iters_out);
+int cvb_dist_stage_ms(cvb_engine *e, double out[5]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,14 @@ def main():
                      "gpu_seconds_total": t_gpu, "cpu_reference_seconds_total": t_cpu,
                      "cpu_kind": type(ref).__name__, "cpu_threads": ref.num_threads()}
         print(json.dumps(out["C3"]), flush=True)
+        if scale == 22:  # the reference's summary of C3, committed as a golden fixture for the GPU test
+            import hashlib
+            gold = {"workload": "R-MAT scale-22 ef16 seed 2, full multi-phase run (main.cpp loop)",
+                    "checker": type(ref).__name__, "level_q": [float(x) for x in want.level_q],
+                    "level_iters": [int(x) for x in want.level_iters], "level_nv": [int(x) for x in want.level_nv],
+                    "comm_sha256": hashlib.sha256(np.ascontiguousarray(want.comm, dtype=np.int64).tobytes()).hexdigest()}
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            json.dump(gold, open(os.path.join(ROOT, "gpurun_out", "c3_rmat22.json"), "w"), indent=1)
         gpu.close()
         del g
         torch.cuda.empty_cache()
