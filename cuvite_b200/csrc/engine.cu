@@ -195,10 +195,18 @@ struct cvb_engine {
   // second-generation kernels (lm.cuh): per-vertex records in class-list order, self-loop weights
   DevBuf<VertexRec> vrec;
   DevBuf<uint32_t> selfw;
+  // "big" path (lm.cuh, partition then hash) for every vertex above 8192 entries
+  DevBuf<int32_t> bg_log2p, bg_item_start, bg_item_owner;
+  DevBuf<uint4> bg_records;
+  DevBuf<uint32_t> bg_cursor, bg_own, bg_cand_key;
+  DevBuf<double> bg_cand_gain;
+  int bg_items = 0;
+  bool use_big = true;         // CVB_BIG=0: first-generation two-pass / global-table kernels
+  bool big_ready = false;
   DevBuf<uint2> mp_stage;      // multi-pass kernel: staged packed records of the 8193..65536 rows
   DevBuf<uint32_t> mp_off, mp_deg;
   DevBuf<int> mp_redo;
-  bool use_mp = true;          // CVB_MP=0: two-pass + global-table kernels for those rows
+  bool use_mp = false;         // CVB_MP=1: serial multi-pass kernel for 8193..65536 (superseded by the big path)
   bool mp_ready = false;
   DevBuf<vid_t> rank, tails_r;  // degree-ordered gather layout (one GPU): rank[v], tails mapped to ranks
   bool remap = false;          // the sweep reads tails_r / rank-ordered packed[]
@@ -210,6 +218,7 @@ struct cvb_engine {
   bool l2_persist = false;     // CVB_L2_PERSIST=1: access-policy window that keeps `packed` persisting in L2 (unmeasured A/B)
   // first degree class that goes through the global tables
   int global_table_class() const {
+    if (use_lm && lm_ready && use_big && big_ready) return kNumClasses;  // nothing goes through the global tables
     if (use_lm && lm_ready && use_mp) return kClsGiant;
     return use_cluster ? kClsGiant : (use_twopass ? kClsC4 : kClsC2);
   }
@@ -408,6 +417,8 @@ int launch_lm_group(cvb_engine *e, cudaStream_t st, const LmParams &p, int64_t f
     e->launches++;
     return CVB_OK;
   };
+  static const bool v4 = [] { const char *s = getenv("CVB_LM4G"); return !(s && s[0] == '0'); }();
+  if (v4) return e->unit_weights ? go(k_lm_group4<G, U, CAPLOG2, true>) : go(k_lm_group4<G, U, CAPLOG2, false>);
   return e->unit_weights ? go(k_lm_group<G, U, CAPLOG2, true>) : go(k_lm_group<G, U, CAPLOG2, false>);
 }
 
@@ -473,6 +484,7 @@ int launch_sweep_u32(cvb_engine *e) {
     q.tails = remap ? e->tails_r.p : e->tails.p;
     q.remap = remap ? 1 : 0;
     q.rank_top = static_cast<int>(e->nvl - 1);
+    q.simple_rows = (e->rows_simple && !getenv("CVB_NO_SINGLETON_SKIP")) ? 1 : 0;
     q.weights = reinterpret_cast<const uint32_t *>(e->weights.p);
     q.packed = e->packed.p;
     q.selfw = e->has_selfloops ? e->selfw.p : nullptr;
@@ -565,7 +577,34 @@ int launch_sweep_u32(cvb_engine *e) {
   // distributed shared memory (correct, but DSMEM moves ~32 B per 4-byte atomic and
   // measured slower on B200 — DESIGN.md section 5).
   const int gcls = e->global_table_class();
-  const bool mp = lm && e->mp_ready;
+  const bool big = lm && e->big_ready;
+  if (big && (n = e->class_start[kClsGiant + 1] - e->class_start[kClsC2]) > 0) {
+    BigParams bp{};
+    bp.chunk_owner = e->big_owner.p;
+    bp.chunk_start = e->big_layout.p;
+    bp.log2p = e->bg_log2p.p;
+    bp.item_start = e->bg_item_start.p;
+    bp.item_owner = e->bg_item_owner.p;
+    bp.records = e->bg_records.p;
+    bp.cursor = e->bg_cursor.p;
+    bp.own = e->bg_own.p;
+    bp.cand_gain = e->bg_cand_gain.p;
+    bp.cand_key = e->bg_cand_key.p;
+    bp.flags = e->d_flags.p;
+    bp.big_first = static_cast<int>(pos(kClsC2));
+    constexpr size_t kStageSmem = size_t(8) << 13, kPassSmem = size_t(8) << 13;
+    auto stage = e->unit_weights ? k_big_stage<true> : k_big_stage<false>;
+    const int occ1 = lm_setup(e, reinterpret_cast<const void *>(stage), 512, kStageSmem);
+    const int occ2 = lm_setup(e, reinterpret_cast<const void *>(k_big_pass), 512, kPassSmem);
+    CVB_CHECK(occ1 > 0 && occ2 > 0, CVB_ERR_CUDA, "big-vertex kernels: cannot configure (%s)",
+              cudaGetErrorString(cudaGetLastError()));
+    const int64_t cap1 = static_cast<int64_t>(e->num_sms) * occ1, cap2 = static_cast<int64_t>(e->num_sms) * occ2;
+    stage<<<static_cast<int>(e->big_chunks < cap1 ? e->big_chunks : cap1), 512, kStageSmem, e->aux[1]>>>(q, bp, e->big_chunks);
+    k_big_pass<<<static_cast<int>(e->bg_items < cap2 ? e->bg_items : cap2), 512, kPassSmem, e->aux[1]>>>(q, bp, e->bg_items);
+    k_big_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(q, bp, static_cast<int>(n));
+    e->launches += 3;
+  }
+  const bool mp = lm && e->mp_ready && !big;
   if (mp && (n = e->class_start[kClsGiant] - e->class_start[kClsC2]) > 0) {
     constexpr size_t smem = lm_multipass_smem();
     auto go = [&](auto kern) -> int {
@@ -580,7 +619,7 @@ int launch_sweep_u32(cvb_engine *e) {
     };
     CVB_TRY(e->unit_weights ? go(k_lm_multipass<true>) : go(k_lm_multipass<false>));
   }
-  if (!mp && !e->use_cluster && e->use_twopass && (n = cnt(kClsC2)) > 0) {
+  if (!mp && !big && !e->use_cluster && e->use_twopass && (n = cnt(kClsC2)) > 0) {
     constexpr int kTwoPassSmem = 16384 * 8;
     if (first_use_on_device(e->device, reinterpret_cast<const void *>(&k_sweep_u32_twopass))) {
       CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_twopass, cudaFuncAttributeMaxDynamicSharedMemorySize, kTwoPassSmem));
@@ -589,7 +628,7 @@ int launch_sweep_u32(cvb_engine *e) {
     k_sweep_u32_twopass<<<grid, 1024, kTwoPassSmem, e->aux[1]>>>(p, lst(kClsC2), static_cast<int>(n));
     e->launches++;
   }
-  if (e->use_cluster && !mp) {
+  if (e->use_cluster && !mp && !big) {
     if ((n = cnt(kClsC8)) > 0) CVB_TRY(launch_cluster<8>(e, e->aux[1], p, lst(kClsC8), n));
     if ((n = cnt(kClsC4)) > 0) CVB_TRY(launch_cluster<4>(e, e->aux[1], p, lst(kClsC4), n));
     if ((n = cnt(kClsC2)) > 0) CVB_TRY(launch_cluster<2>(e, e->aux[1], p, lst(kClsC2), n));
@@ -878,6 +917,47 @@ int post_graph(cvb_engine *e) {
       k_giant_chunk_owner<<<static_cast<int>(nbig), 64, 0, st>>>(e->big_layout.p, (int)nbig, e->big_owner.p);
       e->launches++;
     }
+    // "big" path (partition then hash): partitions, bucket layout and scratch of every vertex above 8192 entries
+    e->big_ready = false;
+    e->bg_items = 0;
+    if (e->lm_ready && e->use_big && nbig > 0 && e->max_degree <= (int64_t(1) << 20)) {
+      std::vector<uint32_t> hdeg(nbig);
+      CVB_TRY(e->mp_deg.ensure(nbig + 1));
+      k_mp_degrees<<<grid_for(nbig, 256), 256, 0, st>>>(e->vrec.p + e->class_start[kClsC2], static_cast<int>(nbig),
+                                                      e->mp_deg.p);
+      e->launches++;
+      CVB_CUDA(cudaMemcpyAsync(hdeg.data(), e->mp_deg.p, nbig * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CVB_CUDA(cudaStreamSynchronize(st));
+      std::vector<int32_t> lp(nbig), istart(nbig + 1), iowner;
+      int items = 0;
+      for (int64_t i = 0; i < nbig; ++i) {
+        int l = 0;
+        while ((static_cast<int64_t>(kBigPartTarget) << l) < static_cast<int64_t>(hdeg[i])) ++l;
+        lp[i] = l;
+        istart[i] = items;
+        items += 1 << l;
+      }
+      istart[nbig] = items;
+      iowner.resize(items);
+      for (int64_t i = 0; i < nbig; ++i)
+        for (int q = istart[i]; q < istart[i + 1]; ++q) iowner[q] = static_cast<int32_t>(i);
+      CVB_TRY(e->bg_log2p.ensure(nbig + 1));
+      CVB_TRY(e->bg_item_start.ensure(nbig + 2));
+      CVB_TRY(e->bg_item_owner.ensure(items + 1));
+      CVB_TRY(e->bg_records.ensure(static_cast<size_t>(items) * kBigBucketCap + 1));
+      CVB_TRY(e->bg_cursor.ensure(items + 1));
+      CVB_TRY(e->bg_own.ensure(nbig + 1));
+      CVB_TRY(e->bg_cand_key.ensure(items + 1));
+      CVB_TRY(e->bg_cand_gain.ensure(items + 1));
+      CVB_CUDA(cudaMemcpyAsync(e->bg_log2p.p, lp.data(), nbig * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CVB_CUDA(cudaMemcpyAsync(e->bg_item_start.p, istart.data(), (nbig + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CVB_CUDA(cudaMemcpyAsync(e->bg_item_owner.p, iowner.data(), items * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CVB_CUDA(cudaMemsetAsync(e->bg_cursor.p, 0, (items + 1) * sizeof(uint32_t), st));
+      CVB_CUDA(cudaMemsetAsync(e->bg_own.p, 0, (nbig + 1) * sizeof(uint32_t), st));
+      CVB_CUDA(cudaStreamSynchronize(st));  // the host vectors go out of scope
+      e->bg_items = items;
+      e->big_ready = true;
+    }
     const int gcls = e->global_table_class();
     const int64_t ngiant = e->class_start[kClsGiant + 1] - e->class_start[gcls];  // global-table vertices
     if (ngiant > 0) {
@@ -1041,7 +1121,8 @@ cvb_engine *cvb_create(void *stream) {
   if (const char *s = getenv("CVB_SPLIT")) e->use_split = (s[0] == '1');
   if (const char *s = getenv("CVB_LM")) e->use_lm = (s[0] != '0');
   if (const char *s = getenv("CVB_REMAP")) e->use_remap = (s[0] != '0');
-  if (const char *s = getenv("CVB_MP")) e->use_mp = (s[0] != '0');
+  if (const char *s = getenv("CVB_MP")) e->use_mp = (s[0] == '1');
+  if (const char *s = getenv("CVB_BIG")) e->use_big = (s[0] != '0');
   if (const char *s = getenv("CVB_BIG_DENSE")) e->big_dense = (s[0] != '0');
   if (const char *s = getenv("CVB_BIG_DENSE_MB")) {
     const long mb = atol(s);
@@ -1090,6 +1171,8 @@ void cvb_destroy(cvb_engine *e) {
   e->h_sums.release(); e->staging.release(); e->staging2.release(); e->giant.release(); e->h_stage.release();
   e->packed.release(); e->giant_layout.release(); e->gslots.release(); e->pair_keys.release(); e->pair_w.release();
   e->cdeg32.release(); e->vrec.release(); e->selfw.release(); e->rank.release(); e->tails_r.release();
+  e->bg_log2p.release(); e->bg_item_start.release(); e->bg_item_owner.release(); e->bg_records.release();
+  e->bg_cursor.release(); e->bg_own.release(); e->bg_cand_key.release(); e->bg_cand_gain.release();
   e->mp_stage.release(); e->mp_off.release(); e->mp_deg.release(); e->mp_redo.release();
   e->dense.release(); e->kcount.release(); e->klist.release(); e->gchunk2_gain.release(); e->gchunk2_key.release();
   e->gmeta.release(); e->gpiece_key.release(); e->gpiece_gain.release(); e->gchunk_gain.release();
@@ -1303,7 +1386,8 @@ static int apply_reduce_async(cvb_engine *e) {
                                                       e->ticket.p, e->d_sums.p);
   e->launches++;
   CVB_CUDA(cudaGetLastError());
-  CVB_CUDA(cudaMemcpyAsync(e->h_sums.p, e->d_sums.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  k_flag_to_f64<<<1, 1, 0, e->stream>>>(e->d_flags.p + 3, e->d_sums.p + 2);  // big-path bucket overflow (never expected)
+  CVB_CUDA(cudaMemcpyAsync(e->h_sums.p, e->d_sums.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   return CVB_OK;
 }
 
@@ -1329,6 +1413,9 @@ int cvb_apply_and_reduce(cvb_engine *e, double sums[2]) {
   CVB_TRY(apply_reduce_async(e));
   CVB_CUDA(cudaStreamSynchronize(e->stream));
   memcpy(sums, e->h_sums.p, 2 * sizeof(double));
+  CVB_CHECK(reinterpret_cast<const double *>(e->h_sums.p)[2] == 0.0, CVB_ERR_CAPACITY,
+            "a partition bucket of the big-vertex path overflowed (community ids colliding in the partition "
+            "hash); rerun with CVB_BIG=0");
   return CVB_OK;
 }
 

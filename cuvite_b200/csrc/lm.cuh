@@ -55,6 +55,7 @@ struct LmParams {
   // vertex at class-list position i has rank rank_top - i.
   int remap;
   int rank_top;
+  int simple_rows;  // every row holds each tail at most once (singleton neighbours bypass the table)
   vid_t *__restrict__ target;  // [nv_local]
   double *__restrict__ cw;     // [nv_local]
   double *__restrict__ ddeg;   // [nv_global] or nullptr (labels-only exchange)
@@ -467,13 +468,118 @@ __host__ __device__ constexpr size_t lm_block4_smem() {
   return (static_cast<size_t>(8) << CAPLOG2) + static_cast<size_t>(64) * TPV;
 }
 
+// Claim phase of one lane (fourth generation): first-probe CAS for each of its nv entries, deferred
+// records for the collisions and their resolution with double hashing.  Returns the mask of entries
+// that opened their community's HOME slot (evaluated later from registers); `skipmask` gets the
+// entries that bypass the table altogether: on graphs whose rows hold each tail once
+// (p.simple_rows), a neighbour whose community is a singleton cannot share it with another entry
+// of the row, so its accumulated weight is its own weight by construction.
+template <int CAPLOG2, int U, bool UNIT>
+__device__ __forceinline__ uint32_t lm4_claim(const LmParams &p, const uint2 (&pk)[U], const uint32_t (&w)[U], int nv,
+                                              uint32_t tbl, uint32_t me_key, int lstride, uint32_t lst0,
+                                              uint32_t &front, int lane_pos, int stride, uint32_t row_e0,
+                                              uint32_t &skipmask) {
+  constexpr uint32_t kMaskB = ((1u << CAPLOG2) - 1u) << 3;
+  front = lst0;                              // claim records grow up
+  uint32_t back = lst0 + (U - 1) * lstride;  // deferred records grow down
+  const uint32_t back0 = back;
+  uint32_t old[U];
+  skipmask = 0u;
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u < nv) {
+      const bool skip = p.simple_rows && (pk[u].x & kSingletonBit) && pk[u].x != me_key;
+      skipmask |= skip ? (1u << u) : 0u;
+      old[u] = skip ? 0u : atoms_cas(tbl + lm_home<CAPLOG2>(pk[u].x), kEmptyKeyU, pk[u].x);
+    }
+  uint32_t freshmask = 0u;
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u < nv && !(skipmask & (1u << u))) {
+      const bool fresh = old[u] == kEmptyKeyU;
+      const bool same = old[u] == pk[u].x;
+      freshmask |= fresh ? (1u << u) : 0u;
+      // unit weights: the slot counts the entries AFTER the claim; weighted: every entry adds
+      if (UNIT ? same : (fresh || same)) reds_add(tbl + lm_home<CAPLOG2>(pk[u].x) + 4u, w[u]);
+      const bool pend = !fresh && !same;
+      sts64_if(pend, back, pk[u].x, UNIT ? pk[u].y : static_cast<uint32_t>(lane_pos + u * stride));
+      back -= pend ? lstride : 0;
+    }
+  // deferred entries, most recent first (a claim record written at the front never lands on an unread
+  // deferred record): double hashing from the home slot
+  for (uint32_t a = back + lstride; a != back0 + lstride; a += lstride) {
+    const uint2 r = lds64(a);
+    const uint32_t key = r.x;
+    uint32_t ay = r.y, wd = 1u;
+    if (!UNIT) {
+      wd = __ldg(p.weights + row_e0 + r.y);
+      ay = __ldg(&p.packed[__ldg(p.tails + row_e0 + r.y)]).y;
+    }
+    uint32_t s2 = lm_home<CAPLOG2>(key);
+    const uint32_t step = (((key * 0x85EBCA6Bu) >> (29 - CAPLOG2)) & kMaskB) | 8u;  // odd number of slots
+    uint32_t o2;
+    do {
+      s2 = (s2 + step) & kMaskB;
+      o2 = atoms_cas(tbl + s2, kEmptyKeyU, key);
+    } while (o2 != kEmptyKeyU && o2 != key);
+    if (!UNIT || o2 == key) reds_add(tbl + s2 + 4u, wd);
+    if (o2 == kEmptyKeyU) {
+      sts64(front, tbl + s2, ay);
+      front += lstride;
+    }
+  }
+  return freshmask;
+}
+
+// Evaluation phase of one lane: the slots it opened (records, then registers) are read and freed.
+template <int CAPLOG2, int U, bool UNIT>
+__device__ __forceinline__ void lm4_eval(const LmParams &p, const uint2 (&pk)[U], const uint32_t (&w)[U],
+                                         uint32_t freshmask, uint32_t skipmask, uint32_t tbl, int lstride, uint32_t lst0,
+                                         uint32_t front, double eix, double vd, double ax, double &g, uint32_t &id) {
+  for (uint32_t a = lst0; a != front; a += lstride) {  // slots opened while resolving deferred entries
+    const uint2 rec = lds64(a);
+    const uint2 kw = lds64(rec.x);
+    sts64(rec.x, kEmptyKeyU, 0u);
+    const uint32_t tot = UNIT ? kw.y + 1u : kw.y;
+    const double g2 = modularity_gain(u32_to_f64(tot), eix, vd, u32_to_f64(rec.y), ax, p.constant);
+    if (lm_better(g2, kw.x, g, id)) {
+      g = g2;
+      id = kw.x;
+    }
+  }
+  uint32_t cnt[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    cnt[u] = 0u;
+    if (freshmask & (1u << u)) cnt[u] = lds_u32(tbl + lm_home<CAPLOG2>(pk[u].x) + 4u);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if ((freshmask | skipmask) & (1u << u)) {
+      if (freshmask & (1u << u)) {
+        const uint32_t so = tbl + lm_home<CAPLOG2>(pk[u].x);
+        if (UNIT) {
+          sts_u32(so, kEmptyKeyU);
+          if (cnt[u] != 0u) sts_u32(so + 4u, 0u);  // rare: a later entry of the same community
+        } else {
+          sts64(so, kEmptyKeyU, 0u);
+        }
+      }
+      const uint32_t tot = (freshmask & (1u << u)) ? (UNIT ? cnt[u] + 1u : cnt[u]) : w[u];
+      const double g2 = modularity_gain(u32_to_f64(tot), eix, vd, u32_to_f64(pk[u].y), ax, p.constant);
+      if (lm_better(g2, pk[u].x, g, id)) {
+        g = g2;
+        id = pk[u].x;
+      }
+    }
+}
+
 template <int TPV, int CAPLOG2, bool UNIT>
 __global__ void __launch_bounds__(TPV, (TPV >= 512 ? 1024 : 768) / TPV) k_lm_block4(LmParams p, int first, int n) {
   constexpr int CAP = 1 << CAPLOG2;
   constexpr int U = 8;
   static_assert(CAP >= 2 * TPV * U, "table too small for the class");
   constexpr uint32_t kTblBytes = CAP * 8u;
-  constexpr uint32_t kMaskB = ((1u << CAPLOG2) - 1u) << 3;
   constexpr int kWarps = TPV / 32;
   extern __shared__ __align__(16) unsigned char lm_smem[];
   __shared__ double red_g[kWarps];
@@ -555,97 +661,24 @@ __global__ void __launch_bounds__(TPV, (TPV >= 512 ? 1024 : 768) / TPV) k_lm_blo
       }
     }
     __syncthreads();  // T: the own community is pre-claimed, every slot of the previous vertex is free
-    // ---- B: first-probe claims of this lane's entries ----
-    uint32_t front = lst0;                     // claim records grow up
-    uint32_t back = lst0 + (U - 1) * lstride;  // deferred records grow down
-    const uint32_t back0 = back;
-    uint32_t old[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (u < nv) old[u] = atoms_cas(tbl + lm_home<CAPLOG2>(pk[u].x), kEmptyKeyU, pk[u].x);
-    uint32_t freshmask = 0u;
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (u < nv) {
-        const bool fresh = old[u] == kEmptyKeyU;
-        const bool same = old[u] == pk[u].x;
-        freshmask |= fresh ? (1u << u) : 0u;
-        // unit weights: the slot counts the entries AFTER the claim; weighted: every entry adds
-        if (UNIT ? same : (fresh || same)) reds_add(tbl + lm_home<CAPLOG2>(pk[u].x) + 4u, w[u]);
-        const bool pend = !fresh && !same;
-        sts64_if(pend, back, pk[u].x, UNIT ? pk[u].y : static_cast<uint32_t>(tid + u * act));
-        back -= pend ? lstride : 0;
-      }
-    // ---- C: gathers of vertex k+1 ----
+    // ---- B: claims (C: the gathers of vertex k+1 are issued before the deferred entries are resolved) ----
     uint2 pkn[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
       if (u < nvn) pkn[u] = __ldg(&p.packed[tn[u]]);
-    // ---- D: deferred entries, most recent first (a claim record written at the front never lands on an
-    //         unread deferred record): double hashing from the home slot ----
-    for (uint32_t a = back + lstride; a != back0 + lstride; a += lstride) {
-      const uint2 r = lds64(a);
-      const uint32_t key = r.x;
-      uint32_t ay = r.y, wd = 1u;
-      if (!UNIT) {
-        wd = __ldg(p.weights + r4.y + r.y);
-        ay = __ldg(&p.packed[__ldg(p.tails + r4.y + r.y)]).y;
-      }
-      uint32_t s2 = lm_home<CAPLOG2>(key);
-      const uint32_t step = (((key * 0x85EBCA6Bu) >> (29 - CAPLOG2)) & kMaskB) | 8u;  // odd number of slots
-      uint32_t o2;
-      do {
-        s2 = (s2 + step) & kMaskB;
-        o2 = atoms_cas(tbl + s2, kEmptyKeyU, key);
-      } while (o2 != kEmptyKeyU && o2 != key);
-      if (!UNIT || o2 == key) reds_add(tbl + s2 + 4u, wd);
-      if (o2 == kEmptyKeyU) {
-        sts64(front, tbl + s2, ay);
-        front += lstride;
-      }
-    }
+    uint32_t front, skipmask;
+    const uint32_t freshmask =
+        lm4_claim<CAPLOG2, U, UNIT>(p, pk, w, nv, tbl, me.x, lstride, lst0, front, tid, act, r4.y, skipmask);
     __syncthreads();  // S1: every entry of the vertex is in the table
     // ---- E: evaluation; each lane reads and frees the slots it opened ----
     const double vd = u32_to_f64(r4.w);
-    const uint32_t c0u = lds_u32(hcc + 4u);
-    const double counter0 = u32_to_f64(c0u);
+    const double counter0 = u32_to_f64(lds_u32(hcc + 4u));
     double eix = counter0;
     if (p.selfw != nullptr) eix = counter0 - u32_to_f64(__ldg(&p.selfw[v]));
     const double ax = u32_to_f64(me.y) - vd;
     double g = -1.0;
     uint32_t id = kLabelMask;
-    for (uint32_t a = lst0; a != front; a += lstride) {  // slots opened while resolving deferred entries
-      const uint2 rec = lds64(a);
-      const uint2 kw = lds64(rec.x);
-      sts64(rec.x, kEmptyKeyU, 0u);
-      const uint32_t tot = UNIT ? kw.y + 1u : kw.y;
-      const double g2 = modularity_gain(u32_to_f64(tot), eix, vd, u32_to_f64(rec.y), ax, p.constant);
-      if (lm_better(g2, kw.x, g, id)) {
-        g = g2;
-        id = kw.x;
-      }
-    }
-    uint32_t cnt[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (freshmask & (1u << u)) cnt[u] = lds_u32(tbl + lm_home<CAPLOG2>(pk[u].x) + 4u);
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (freshmask & (1u << u)) {
-        const uint32_t so = tbl + lm_home<CAPLOG2>(pk[u].x);
-        if (UNIT) {
-          sts_u32(so, kEmptyKeyU);
-          if (cnt[u] != 0u) sts_u32(so + 4u, 0u);  // rare: a later entry of the same community
-        } else {
-          sts64(so, kEmptyKeyU, 0u);
-        }
-        const uint32_t tot = UNIT ? cnt[u] + 1u : cnt[u];
-        const double g2 = modularity_gain(u32_to_f64(tot), eix, vd, u32_to_f64(pk[u].y), ax, p.constant);
-        if (lm_better(g2, pk[u].x, g, id)) {
-          g = g2;
-          id = pk[u].x;
-        }
-      }
+    lm4_eval<CAPLOG2, U, UNIT>(p, pk, w, freshmask, skipmask, tbl, lstride, lst0, front, eix, vd, ax, g, id);
     double wg;
     uint32_t wid = warp_argmax(g, id, &wg);
     if (lane == 0) {
@@ -675,6 +708,100 @@ __global__ void __launch_bounds__(TPV, (TPV >= 512 ? 1024 : 768) / TPV) k_lm_blo
       pk[u] = pkn[u];
       w[u] = wn[u];
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Fourth-generation group kernel: G lanes per vertex, at most U entries per lane, 32/G vertices per
+// warp — same claim / evaluate scheme as k_lm_block4 with __syncwarp in place of the block barriers,
+// and the record + own packed entry of the warp's next batch fetched one batch ahead.
+// Shared memory per vertex: 8 * CAP (table) + 8 * G * U (records).
+// ---------------------------------------------------------------------------
+template <int G, int U, int CAPLOG2, bool UNIT>
+__global__ void __launch_bounds__(256, 3) k_lm_group4(LmParams p, int first, int n) {
+  constexpr int NG = 32 / G;
+  constexpr int CAP = 1 << CAPLOG2;
+  static_assert(CAP >= 2 * G * U, "table too small for the class");
+  constexpr uint32_t kTblBytes = CAP * 8u, kListBytes = G * U * 8u;
+  constexpr int LSTRIDE = G * 8;
+  extern __shared__ __align__(16) unsigned char lm_smem[];
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = static_cast<int>(threadIdx.x >> 5);
+  const int grp = static_cast<int>(lane) / G, lig = static_cast<int>(lane) % G;
+  const uint32_t smem0 = smem_addr(lm_smem);
+  const uint32_t tbl = smem0 + static_cast<uint32_t>(wib * NG + grp) * kTblBytes;
+  const uint32_t lst0 = smem0 + 8u * NG * kTblBytes + static_cast<uint32_t>(wib * NG + grp) * kListBytes +
+                        static_cast<uint32_t>(lig) * 8u;
+  for (int s = lig; s < CAP; s += G) sts64(tbl + s * 8u, kEmptyKeyU, 0u);
+  __syncwarp();
+
+  const int nbatch = (n + NG - 1) / NG;
+  const int bstride = gridDim.x * 8;
+  int b = blockIdx.x * 8 + wib;
+  if (b >= nbatch) return;
+  auto fetch = [&](int batch, uint4 &r, uint2 &m, bool &lv) {
+    const int it = batch * NG + grp;
+    lv = batch < nbatch && it < n;
+    r = lv ? __ldg(reinterpret_cast<const uint4 *>(p.vrec + first + it)) : make_uint4(0u, 0u, 0u, 0u);
+    m = __ldg(&p.packed[lv ? lm_self(p, r.x, first + it) : 0u]);
+  };
+  uint4 r4;
+  uint2 me;
+  bool live;
+  fetch(b, r4, me, live);
+  for (; b < nbatch; b += bstride) {
+    uint4 r4n;
+    uint2 men;
+    bool liven;
+    fetch(b + bstride, r4n, men, liven);
+    const vid_t v = static_cast<vid_t>(r4.x);
+    const int deg = static_cast<int>(r4.z);
+    const uint32_t hcc = tbl + lm_home<CAPLOG2>(me.x);
+    if (live && lig == 0) sts_u32(hcc, me.x);  // pre-claim the own community: counter[0] lives in its home slot
+    int nv = (deg - lig + G - 1) / G;
+    nv = nv < 0 ? 0 : (nv > U ? U : nv);
+    uint2 pk[U];
+    uint32_t w[U];
+    {
+      uint32_t t[U];
+      const vid_t *__restrict__ row = p.tails + r4.y;
+      const uint32_t *__restrict__ wrow = p.weights + r4.y;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        t[u] = 0u;
+        w[u] = 1u;
+        if (u < nv) {
+          t[u] = static_cast<uint32_t>(__ldcs(row + lig + u * G));
+          if (!UNIT) w[u] = __ldcs(wrow + lig + u * G);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (u < nv) pk[u] = __ldg(&p.packed[t[u]]);
+    }
+    __syncwarp();
+    uint32_t front, skipmask;
+    const uint32_t freshmask =
+        lm4_claim<CAPLOG2, U, UNIT>(p, pk, w, nv, tbl, me.x, LSTRIDE, lst0, front, lig, G, r4.y, skipmask);
+    __syncwarp();
+    const double vd = u32_to_f64(r4.w);
+    const double counter0 = u32_to_f64(lds_u32(hcc + 4u));
+    double eix = counter0;
+    if (p.selfw != nullptr && live) eix = counter0 - u32_to_f64(__ldg(&p.selfw[v]));
+    const double ax = u32_to_f64(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+    lm4_eval<CAPLOG2, U, UNIT>(p, pk, w, freshmask, skipmask, tbl, LSTRIDE, lst0, front, eix, vd, ax, g, id);
+    double wg;
+    const uint32_t wid = lm_group_argmax<G>(g, id, &wg);
+    if (live && lig == 0) {
+      lm_commit(p, v, me.x, wg, wid, vd, counter0);
+      sts64(hcc, kEmptyKeyU, 0u);
+    }
+    __syncwarp();
+    r4 = r4n;
+    me = men;
+    live = liven;
   }
 }
 
@@ -864,6 +991,255 @@ __global__ void __launch_bounds__(1024, 1) k_lm_multipass(LmParams p, int first,
       sts_u32(meta + 12u, 0u);
     }
     __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Vertices above 8192 entries: partition, then hash ("big" path, three kernels).
+//
+//  k_big_stage  one CTA per 4096-entry CHUNK of a big row (all SMs work on the same hub): tails ->
+//               packed gather -> merge of the chunk in a shared-memory table (duplicates inside a
+//               chunk collapse, so a community contributes at most one record per chunk) -> every
+//               distinct {community, weight, community degree} record is appended to the bucket of
+//               the community's PARTITION (a hash of the community id; P = deg/2048 rounded up to a
+//               power of two partitions per vertex) in global memory.  Bucket positions come from one
+//               shared-memory counter per partition and ONE global atomic per (chunk, partition).
+//               Entries of the vertex's own community add to a per-vertex counter instead.
+//  k_big_pass   one CTA per (vertex, partition) bucket: at most 4096 records, read coalesced, merged
+//               in an 8192-slot shared-memory table, evaluated; one (gain, community) candidate per
+//               bucket.
+//  k_big_final  one warp per vertex: best of its P candidates, commit, reset of the cursors.
+// Nothing touches an L2-resident global hash table (the first generation's global-table path ran
+// these vertices at ~15 G entries/s, 4.3 of the 9.9 ms of a scale-24 sweep); the work of one hub is
+// spread over deg/4096 CTAs in the first kernel and P CTAs in the second.
+// A bucket holds 4096 records, twice the expected load of the fullest partition; a fuller bucket
+// (keys engineered to collide in the partition hash) sets flags[3] and the host reports it.
+// ---------------------------------------------------------------------------
+constexpr int kBigChunk = 4096;      // == kGiantChunk: the chunk layout of the first-sweep kernels is shared
+constexpr int kBigBucketCap = 4096;  // records per (vertex, partition): twice the expected load of the fullest one
+constexpr int kBigPartTarget = 2048; // expected records per partition at most
+constexpr int kBigMaxParts = 512;    // deg <= 2^20
+
+struct BigParams {
+  const int32_t *__restrict__ chunk_owner;  // [chunks] big-vertex index of every chunk
+  const int64_t *__restrict__ chunk_start;  // [nbig+1]
+  const int32_t *__restrict__ log2p;        // [nbig] partitions of each vertex (log2)
+  const int32_t *__restrict__ item_start;   // [nbig+1] first bucket of each vertex
+  const int32_t *__restrict__ item_owner;   // [items] big-vertex index of every bucket
+  uint4 *__restrict__ records;              // [items * kBigBucketCap] {key, weight, community degree, -}
+  uint32_t *__restrict__ cursor;            // [items] records in each bucket
+  uint32_t *__restrict__ own;               // [nbig] weight of the entries of the vertex's own community
+  double *__restrict__ cand_gain;           // [items]
+  uint32_t *__restrict__ cand_key;          // [items]
+  int *__restrict__ flags;                  // flags[3] |= 1 on bucket overflow
+  int big_first;                            // class-list position of the first big vertex
+};
+
+__device__ __forceinline__ uint32_t big_part(uint32_t key, int log2p) {
+  return log2p == 0 ? 0u : ((key & kLabelMask) * 0xC2B2AE35u) >> (32 - log2p);
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(512, 2) k_big_stage(LmParams p, BigParams b, int64_t total_chunks) {
+  constexpr int TPB = 512, U = kBigChunk / TPB, CAPLOG2 = 13;
+  constexpr uint32_t kMaskB = ((1u << CAPLOG2) - 1u) << 3;
+  extern __shared__ __align__(16) unsigned char lm_smem[];  // 8192-slot table (64 KB)
+  __shared__ uint32_t pcount[kBigMaxParts], pbase[kBigMaxParts];
+  const int tid = static_cast<int>(threadIdx.x);
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t tbl = smem_addr(lm_smem);
+  for (int s = tid; s < (1 << CAPLOG2); s += TPB) sts64(tbl + s * 8u, kEmptyKeyU, 0u);
+  if (tid < kBigMaxParts) pcount[tid] = 0u;
+  __syncthreads();
+  for (int64_t chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    const int bi = b.chunk_owner[chunk];
+    const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(p.vrec + b.big_first + bi));
+    const uint2 me = __ldg(&p.packed[lm_self(p, r4.x, b.big_first + bi)]);
+    const int lp = b.log2p[bi];
+    const int c0 = static_cast<int>(chunk - b.chunk_start[bi]) * kBigChunk;
+    const int cn = (static_cast<int>(r4.z) - c0) < kBigChunk ? (static_cast<int>(r4.z) - c0) : kBigChunk;
+    const vid_t *__restrict__ row = p.tails + r4.y + c0;
+    const uint32_t *__restrict__ wrow = p.weights + r4.y + c0;
+    uint2 pk[U];
+    uint32_t w[U], so[U], t[U];
+    int nv = (cn - tid + TPB - 1) / TPB;
+    nv = nv < 0 ? 0 : (nv > U ? U : nv);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      t[u] = 0u;
+      w[u] = 1u;
+      if (u < nv) {
+        t[u] = static_cast<uint32_t>(__ldcs(row + tid + u * TPB));
+        if (!UNIT) w[u] = __ldcs(wrow + tid + u * TPB);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < nv) pk[u] = __ldg(&p.packed[t[u]]);
+    // merge the chunk: claims stay in registers (slot address per entry)
+    uint32_t claimed = 0u, ownsum = 0u;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      so[u] = 0u;
+      if (u < nv) {
+        const uint32_t key = pk[u].x;
+        if (key == me.x) {
+          ownsum += w[u];
+        } else {
+          uint32_t s2 = lm_home<CAPLOG2>(key);
+          const uint32_t step = (((key * 0x85EBCA6Bu) >> (29 - CAPLOG2)) & kMaskB) | 8u;
+          uint32_t o2 = atoms_cas(tbl + s2, kEmptyKeyU, key);
+          while (o2 != kEmptyKeyU && o2 != key) {
+            s2 = (s2 + step) & kMaskB;
+            o2 = atoms_cas(tbl + s2, kEmptyKeyU, key);
+          }
+          so[u] = tbl + s2;
+          reds_add(so[u] + 4u, w[u]);
+          claimed |= (o2 == kEmptyKeyU) ? (1u << u) : 0u;
+        }
+      }
+    }
+    ownsum = __reduce_add_sync(0xffffffffu, ownsum);
+    if (lane == 0 && ownsum) atomicAdd(&b.own[bi], ownsum);
+    __syncthreads();  // the chunk is merged
+    // distinct records of this lane: total weight, partition, position inside the CTA's share of the bucket
+    uint32_t tot[U], loc[U], part[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (claimed & (1u << u)) {
+        tot[u] = lds_u32(so[u] + 4u);
+        sts64(so[u], kEmptyKeyU, 0u);
+        part[u] = big_part(pk[u].x, lp);
+        loc[u] = atomicAdd(&pcount[part[u]], 1u);
+      }
+    __syncthreads();
+    if (tid < (1 << lp)) {
+      const uint32_t c = pcount[tid];
+      pbase[tid] = c ? atomicAdd(&b.cursor[b.item_start[bi] + tid], c) : 0u;
+      pcount[tid] = 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (claimed & (1u << u)) {
+        const uint32_t pos = pbase[part[u]] + loc[u];
+        if (pos < static_cast<uint32_t>(kBigBucketCap))
+          b.records[static_cast<int64_t>(b.item_start[bi] + part[u]) * kBigBucketCap + pos] =
+              make_uint4(pk[u].x, tot[u], pk[u].y, 0u);
+        else
+          atomicOr(&b.flags[3], 1);
+      }
+    __syncthreads();  // pbase is reused by the next chunk
+  }
+}
+
+__global__ void __launch_bounds__(512, 2) k_big_pass(LmParams p, BigParams b, int nitems) {
+  constexpr int TPB = 512, U = kBigBucketCap / TPB, CAPLOG2 = 13;
+  constexpr uint32_t kMaskB = ((1u << CAPLOG2) - 1u) << 3;
+  extern __shared__ __align__(16) unsigned char lm_smem[];  // 8192-slot table (64 KB)
+  __shared__ double red_g[TPB / 32];
+  __shared__ uint32_t red_id[TPB / 32];
+  const int tid = static_cast<int>(threadIdx.x);
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = tid >> 5;
+  const uint32_t tbl = smem_addr(lm_smem);
+  for (int s = tid; s < (1 << CAPLOG2); s += TPB) sts64(tbl + s * 8u, kEmptyKeyU, 0u);
+  __syncthreads();
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int bi = b.item_owner[item];
+    uint32_t n = __ldcg(&b.cursor[item]);
+    n = n > static_cast<uint32_t>(kBigBucketCap) ? static_cast<uint32_t>(kBigBucketCap) : n;
+    const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(p.vrec + b.big_first + bi));
+    const vid_t v = static_cast<vid_t>(r4.x);
+    const uint2 me = __ldg(&p.packed[lm_self(p, r4.x, b.big_first + bi)]);
+    const uint4 *__restrict__ rec = b.records + static_cast<int64_t>(item) * kBigBucketCap;
+    uint4 r[U];
+    uint32_t so[U];
+    int nv = (static_cast<int>(n) - tid + TPB - 1) / TPB;
+    nv = nv < 0 ? 0 : (nv > U ? U : nv);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < nv) r[u] = __ldcg(rec + tid + u * TPB);
+    uint32_t claimed = 0u;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      so[u] = 0u;
+      if (u < nv) {
+        const uint32_t key = r[u].x;
+        uint32_t s2 = lm_home<CAPLOG2>(key);
+        const uint32_t step = (((key * 0x85EBCA6Bu) >> (29 - CAPLOG2)) & kMaskB) | 8u;
+        uint32_t o2 = atoms_cas(tbl + s2, kEmptyKeyU, key);
+        while (o2 != kEmptyKeyU && o2 != key) {
+          s2 = (s2 + step) & kMaskB;
+          o2 = atoms_cas(tbl + s2, kEmptyKeyU, key);
+        }
+        so[u] = tbl + s2;
+        reds_add(so[u] + 4u, r[u].y);
+        claimed |= (o2 == kEmptyKeyU) ? (1u << u) : 0u;
+      }
+    }
+    __syncthreads();  // the bucket is merged
+    const double vd = u32_to_f64(r4.w);
+    const double counter0 = u32_to_f64(__ldcg(&b.own[bi]));
+    double eix = counter0;
+    if (p.selfw != nullptr) eix = counter0 - u32_to_f64(__ldg(&p.selfw[v]));
+    const double ax = u32_to_f64(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (claimed & (1u << u)) {
+        const uint32_t tot = lds_u32(so[u] + 4u);
+        sts64(so[u], kEmptyKeyU, 0u);
+        const double g2 = modularity_gain(u32_to_f64(tot), eix, vd, u32_to_f64(r[u].z), ax, p.constant);
+        if (lm_better(g2, r[u].x, g, id)) {
+          g = g2;
+          id = r[u].x;
+        }
+      }
+    double wg;
+    uint32_t wid = warp_argmax(g, id, &wg);
+    if (lane == 0) {
+      red_g[wib] = wg;
+      red_id[wib] = wid;
+    }
+    __syncthreads();  // every slot is free again
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 1; i < TPB / 32; ++i)
+        if (lm_better(red_g[i], red_id[i], wg, wid)) {
+          wg = red_g[i];
+          wid = red_id[i];
+        }
+      b.cand_gain[item] = wg;
+      b.cand_key[item] = wid;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(128) k_big_final(LmParams p, BigParams b, int nbig) {
+  const int bi = static_cast<int>((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+  const unsigned lane = threadIdx.x & 31u;
+  if (bi >= nbig) return;
+  const uint4 r4 = __ldg(reinterpret_cast<const uint4 *>(p.vrec + b.big_first + bi));
+  const uint2 me = __ldg(&p.packed[lm_self(p, r4.x, b.big_first + bi)]);
+  double g = -1.0;
+  uint32_t id = kLabelMask;
+  for (int q = b.item_start[bi] + static_cast<int>(lane); q < b.item_start[bi + 1]; q += 32) {
+    const double g2 = b.cand_gain[q];
+    const uint32_t k2 = b.cand_key[q];
+    if (lm_better(g2, k2, g, id)) {
+      g = g2;
+      id = k2;
+    }
+    b.cursor[q] = 0u;
+  }
+  double wg;
+  const uint32_t wid = warp_argmax(g, id, &wg);
+  if (lane == 0) {
+    lm_commit(p, static_cast<vid_t>(r4.x), me.x, wg, wid, u32_to_f64(r4.w), u32_to_f64(b.own[bi]));
+    b.own[bi] = 0u;
   }
 }
 

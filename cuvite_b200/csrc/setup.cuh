@@ -59,6 +59,8 @@ __global__ void k_convert_edges(const void *__restrict__ aos, const int64_t *__r
   }
 }
 
+__global__ void k_flag_to_f64(const int *__restrict__ flag, double *__restrict__ out) { out[0] = flag[0] ? 1.0 : 0.0; }
+
 __global__ void k_fill_u32(uint32_t *__restrict__ dst, int64_t n, uint32_t v) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
