@@ -66,6 +66,8 @@ SIGNATURES = {
     "cvb_graph_load_vite": (_i32, [_vp, C.c_char_p, _i32, _i32, _i32, C.POINTER(VitePart)]),
     "cvb_louvain_run": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "cvb_louvain_run_ex": (_i32, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "cvb_phase_run_et": (_i32, [_vp, _f64, _f64, _i32, _f64, C.POINTER(_f64), C.POINTER(_i32)]),
+    "cvb_louvain_run_et": (_i32, [_vp, _i32, _i32, _i32, _f64, _vp, _vp, _vp, _vp]),
     "cvb_dist_unique_id": (_i32, [_vp, _i32]),
     "cvb_dist_init": (_i32, [_vp, _vp, _i32, _i32, _i32]),
     "cvb_dist_finalize": (_i32, [_vp]),

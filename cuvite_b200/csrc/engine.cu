@@ -211,7 +211,8 @@ struct cvb_engine {
   DevBuf<vid_t> rank, tails_r;  // degree-ordered gather layout (one GPU): rank[v], tails mapped to ranks
   bool remap = false;          // the sweep reads tails_r / rank-ordered packed[]
   bool use_remap = true;       // CVB_REMAP=0 disables it
-  bool use_lm = true;          // CVB_LM=0: first-generation hash/group kernels
+  bool use_lm = true;          // CVB_LM=0: first-generation hash/group kernels only
+  uint32_t lm_mask = (1u << kClsG8) | (1u << kClsG16) | (1u << kClsG32) | (1u << kClsH16K);  // classes on lm.cuh
   bool lm_ready = false;       // vrec/selfw built for the current graph (U32 mode, < 2^32 entries)
   bool unit_weights = false;   // every weight == 1: the sweep never reads the weights array
   bool has_selfloops = false;
@@ -231,6 +232,12 @@ struct cvb_engine {
   cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr, nullptr};
 
   DistState dist;  // N > 1: NCCL communicator and vertex ranges (dist.cuh)
+  // early termination (cvb_phase_run_et)
+  bool et_no_deltas = false;
+  DevBuf<unsigned char> et_active;
+  DevBuf<vid_t> et_frozen_target;
+  DevBuf<double> et_frozen_cw, et_p[2];
+  DevBuf<unsigned int> et_count;
 
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -294,8 +301,8 @@ int launch_sweep(cvb_engine *e) {
   p.base = static_cast<vid_t>(e->base);
   p.target = e->lab[e->targ].p;
   p.cw = e->cw.p;
-  p.ddeg = e->labels_only ? nullptr : e->ddeg.p;
-  p.dsize = e->labels_only ? nullptr : e->dsize.p;
+  p.ddeg = (e->labels_only || e->et_no_deltas) ? nullptr : e->ddeg.p;
+  p.dsize = (e->labels_only || e->et_no_deltas) ? nullptr : e->dsize.p;
   auto cnt = [&](int c) { return e->class_start[c + 1] - e->class_start[c]; };
   auto lst = [&](int c) { return e->list.p + e->class_start[c]; };
   int64_t n;
@@ -464,8 +471,8 @@ int launch_sweep_u32(cvb_engine *e) {
   p.base = static_cast<vid_t>(e->base);
   p.target = e->lab[e->targ].p;
   p.cw = e->cw.p;
-  p.ddeg = e->labels_only ? nullptr : e->ddeg.p;  // labels-only exchange derives the deltas from labels
-  p.dsize = e->labels_only ? nullptr : e->dsize.p;
+  p.ddeg = (e->labels_only || e->et_no_deltas) ? nullptr : e->ddeg.p;  // labels-only exchange derives the deltas from labels
+  p.dsize = (e->labels_only || e->et_no_deltas) ? nullptr : e->dsize.p;
   p.labels = e->sweep_labels();
   p.csize = e->csize.p;
   p.cdeg32 = nullptr;
@@ -482,7 +489,8 @@ int launch_sweep_u32(cvb_engine *e) {
   if (lm) {
     q.vrec = e->vrec.p;
     q.tails = remap ? e->tails_r.p : e->tails.p;
-    q.remap = remap ? 1 : 0;
+    q.remap = remap ? (e->nvl == e->nvg ? 1 : 2) : 0;
+    q.rank = e->rank.p;
     q.rank_top = static_cast<int>(e->nvl - 1);
     q.simple_rows = (e->rows_simple && !getenv("CVB_NO_SINGLETON_SKIP")) ? 1 : 0;
     q.weights = reinterpret_cast<const uint32_t *>(e->weights.p);
@@ -559,19 +567,24 @@ int launch_sweep_u32(cvb_engine *e) {
   }
   CVB_CUDA(cudaEventRecord(e->ev_fork, st));
   for (int i = 0; i < cvb_engine::kAux; ++i) CVB_CUDA(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
+  // Which generation serves a degree class is decided per class from the measurements of round 2
+  // (profiles/r02_*: R-MAT scale 20 and 24): the second-generation kernels (lm.cuh) win on the small
+  // classes (5..32 entries: per-vertex records, sub-warp groups without match.any), on 4097..8192 and,
+  // with the partition-then-hash path, on everything above 8192; the first-generation hash kernels
+  // (eight register-resident claims per thread, two-deep header pipeline) stay faster from 33 to 4096.
+  // CVB_LM_MASK overrides (bit c = class c on lm.cuh).
+  const uint32_t lm_mask = lm ? e->lm_mask : 0u;
+  auto on_lm = [&](int c) { return ((lm_mask >> c) & 1u) != 0u; };
   // hash classes: 8 CSR entries per thread, TPV = upper degree / 8 threads per vertex
   // stream 0: block-per-vertex classes, largest vertices first
-  if (lm) {
-    CVB_TRY((launch_lm_block<1024, 14>(e, e->aux[0], q, pos(kClsH16K), cnt(kClsH16K))));
-    CVB_TRY((launch_lm_block<512, 13>(e, e->aux[0], q, pos(kClsH8K), cnt(kClsH8K))));
-    CVB_TRY((launch_lm_block<256, 12>(e, e->aux[0], q, pos(kClsH4K), cnt(kClsH4K))));
-    CVB_TRY((launch_lm_block<128, 11>(e, e->aux[0], q, pos(kClsH2K), cnt(kClsH2K))));
-  } else {
-  if ((n = cnt(kClsH16K)) > 0) CVB_TRY((launch_hash<1024, 4, 2, 1>(e, e->aux[0], p, lst(kClsH16K), n)));
-  if ((n = cnt(kClsH8K)) > 0) CVB_TRY((launch_hash<512, 4, 2, 2>(e, e->aux[0], p, lst(kClsH8K), n)));
-  if ((n = cnt(kClsH4K)) > 0) CVB_TRY((launch_hash<256, 4, 2, 4>(e, e->aux[0], p, lst(kClsH4K), n)));
-  if ((n = cnt(kClsH2K)) > 0) CVB_TRY((launch_hash<128, 4, 2, 8>(e, e->aux[0], p, lst(kClsH2K), n)));
-  }
+  if (on_lm(kClsH16K)) CVB_TRY((launch_lm_block<1024, 14>(e, e->aux[0], q, pos(kClsH16K), cnt(kClsH16K))));
+  else if ((n = cnt(kClsH16K)) > 0) CVB_TRY((launch_hash<1024, 4, 2, 1>(e, e->aux[0], p, lst(kClsH16K), n)));
+  if (on_lm(kClsH8K)) CVB_TRY((launch_lm_block<512, 13>(e, e->aux[0], q, pos(kClsH8K), cnt(kClsH8K))));
+  else if ((n = cnt(kClsH8K)) > 0) CVB_TRY((launch_hash<512, 4, 2, 2>(e, e->aux[0], p, lst(kClsH8K), n)));
+  if (on_lm(kClsH4K)) CVB_TRY((launch_lm_block<256, 12>(e, e->aux[0], q, pos(kClsH4K), cnt(kClsH4K))));
+  else if ((n = cnt(kClsH4K)) > 0) CVB_TRY((launch_hash<256, 4, 2, 4>(e, e->aux[0], p, lst(kClsH4K), n)));
+  if (on_lm(kClsH2K)) CVB_TRY((launch_lm_block<128, 11>(e, e->aux[0], q, pos(kClsH2K), cnt(kClsH2K))));
+  else if ((n = cnt(kClsH2K)) > 0) CVB_TRY((launch_hash<128, 4, 2, 8>(e, e->aux[0], p, lst(kClsH2K), n)));
   // stream 1: vertices above 8192 entries.  Default: global (L2-resident) tables for all of
   // them; CVB_CLUSTER=1 routes 8193..65536 to thread-block clusters with the table in
   // distributed shared memory (correct, but DSMEM moves ~32 B per 4-byte atomic and
@@ -691,41 +704,28 @@ int launch_sweep_u32(cvb_engine *e) {
     e->launches += 1;
     }
   }
-  if (lm) {
-    // stream 2: 129..512; stream 3: 5..128
-    CVB_TRY((launch_lm_block<64, 10>(e, e->aux[2], q, pos(kClsH1K), cnt(kClsH1K))));
-    CVB_TRY((launch_lm_group<32, 8, 9>(e, e->aux[2], q, pos(kClsH512), cnt(kClsH512))));
-    CVB_TRY((launch_lm_group<16, 8, 8>(e, e->aux[3], q, pos(kClsH256), cnt(kClsH256))));
-    CVB_TRY((launch_lm_group<8, 8, 7>(e, e->aux[3], q, pos(kClsH128), cnt(kClsH128))));
-    CVB_TRY((launch_lm_group<4, 8, 6>(e, e->aux[3], q, pos(kClsG32), cnt(kClsG32))));
-    CVB_TRY((launch_lm_group<4, 4, 5>(e, e->aux[3], q, pos(kClsG16), cnt(kClsG16))));
-    CVB_TRY((launch_lm_group<2, 4, 4>(e, e->aux[3], q, pos(kClsG8), cnt(kClsG8))));
-    if ((n = cnt(kClsG4)) > 0) {
-      k_sweep_u32_t4<<<static_cast<int>((n + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG4), (int)n);
-      e->launches++;
-    }
-    for (int i = 0; i < cvb_engine::kAux; ++i) {
-      CVB_CUDA(cudaEventRecord(e->ev_join[i], e->aux[i]));
-      CVB_CUDA(cudaStreamWaitEvent(st, e->ev_join[i], 0));
-    }
-    CVB_CUDA(cudaGetLastError());
-    return CVB_OK;
-  }
-  // stream 2: warp-level and sub-warp hash classes
-  if ((n = cnt(kClsH1K)) > 0) CVB_TRY((launch_hash<64, 4, 2, 16>(e, e->aux[2], p, lst(kClsH1K), n)));
-  if ((n = cnt(kClsH512)) > 0) CVB_TRY((launch_hash<32, 4, 2, 4>(e, e->aux[2], p, lst(kClsH512), n)));
-  if ((n = cnt(kClsH256)) > 0) CVB_TRY((launch_hash<32, 4, 1, 4>(e, e->aux[2], p, lst(kClsH256), n)));
-  if ((n = cnt(kClsH128)) > 0) CVB_TRY((launch_hash<32, 2, 1, 4>(e, e->aux[2], p, lst(kClsH128), n)));
-  // stream 3: the small classes
-  if ((n = cnt(kClsG32)) > 0) {
+  // stream 2: 129..512
+  if (on_lm(kClsH1K)) CVB_TRY((launch_lm_block<64, 10>(e, e->aux[2], q, pos(kClsH1K), cnt(kClsH1K))));
+  else if ((n = cnt(kClsH1K)) > 0) CVB_TRY((launch_hash<64, 4, 2, 16>(e, e->aux[2], p, lst(kClsH1K), n)));
+  if (on_lm(kClsH512)) CVB_TRY((launch_lm_group<32, 8, 9>(e, e->aux[2], q, pos(kClsH512), cnt(kClsH512))));
+  else if ((n = cnt(kClsH512)) > 0) CVB_TRY((launch_hash<32, 4, 2, 4>(e, e->aux[2], p, lst(kClsH512), n)));
+  // stream 3: 1..128
+  if (on_lm(kClsH256)) CVB_TRY((launch_lm_group<16, 8, 8>(e, e->aux[3], q, pos(kClsH256), cnt(kClsH256))));
+  else if ((n = cnt(kClsH256)) > 0) CVB_TRY((launch_hash<32, 4, 1, 4>(e, e->aux[3], p, lst(kClsH256), n)));
+  if (on_lm(kClsH128)) CVB_TRY((launch_lm_group<8, 8, 7>(e, e->aux[3], q, pos(kClsH128), cnt(kClsH128))));
+  else if ((n = cnt(kClsH128)) > 0) CVB_TRY((launch_hash<32, 2, 1, 4>(e, e->aux[3], p, lst(kClsH128), n)));
+  if (on_lm(kClsG32)) CVB_TRY((launch_lm_group<4, 8, 6>(e, e->aux[3], q, pos(kClsG32), cnt(kClsG32))));
+  else if ((n = cnt(kClsG32)) > 0) {
     k_sweep_u32_group<32><<<static_cast<int>((n * 32 + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG32), (int)n);
     e->launches++;
   }
-  if ((n = cnt(kClsG16)) > 0) {
+  if (on_lm(kClsG16)) CVB_TRY((launch_lm_group<4, 4, 5>(e, e->aux[3], q, pos(kClsG16), cnt(kClsG16))));
+  else if ((n = cnt(kClsG16)) > 0) {
     k_sweep_u32_group<16><<<static_cast<int>((n * 16 + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG16), (int)n);
     e->launches++;
   }
-  if ((n = cnt(kClsG8)) > 0) {
+  if (on_lm(kClsG8)) CVB_TRY((launch_lm_group<2, 4, 4>(e, e->aux[3], q, pos(kClsG8), cnt(kClsG8))));
+  else if ((n = cnt(kClsG8)) > 0) {
     k_sweep_u32_group<8><<<static_cast<int>((n * 8 + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG8), (int)n);
     e->launches++;
   }
@@ -1120,6 +1120,7 @@ cvb_engine *cvb_create(void *stream) {
   if (const char *s = getenv("CVB_L2_PERSIST")) e->l2_persist = (s[0] == '1');
   if (const char *s = getenv("CVB_SPLIT")) e->use_split = (s[0] == '1');
   if (const char *s = getenv("CVB_LM")) e->use_lm = (s[0] != '0');
+  if (const char *s = getenv("CVB_LM_MASK")) e->lm_mask = static_cast<uint32_t>(strtoul(s, nullptr, 0));
   if (const char *s = getenv("CVB_REMAP")) e->use_remap = (s[0] != '0');
   if (const char *s = getenv("CVB_MP")) e->use_mp = (s[0] == '1');
   if (const char *s = getenv("CVB_BIG")) e->use_big = (s[0] != '0');
@@ -1939,8 +1940,83 @@ int cvb_louvain_run(cvb_engine *e, int max_levels, double *level_q, int *level_i
   return cvb_louvain_run_ex(e, max_levels, 0, level_q, level_iters, level_nv, comm_out);
 }
 
+// distLouvainMethod with early termination (louvain.cpp:7-204 for et_type 1 / 3, 206-423 for 2 / 4) on one
+// GPU.  The sweep kernels are the ordinary ones; they run with the community-delta atomics switched
+// off and k_et_fix adds the deltas of the ACTIVE vertices only and gives the frozen ones their frozen
+// target / clusterWeight back, so every kernel generation serves this mode unchanged.  Labels rotate
+// per vertex (k_et_rotate), not by pointer.
+int cvb_phase_run_et(cvb_engine *e, double lower, double thresh, int et_type, double et_delta, double *q_out,
+                     int *iters_out) {
+  CVB_CHECK(e && e->graph_ready, CVB_ERR_STATE, "cvb_phase_run_et: no graph uploaded");
+  CVB_CHECK(e->nvl == e->nvg, CVB_ERR_STATE, "cvb_phase_run_et is the one-GPU driver");
+  CVB_CHECK(et_type >= 1 && et_type <= 4, CVB_ERR_ARG, "early-termination type must be 1..4 (option -t)");
+  CVB_CHECK(!(et_type == 2 || et_type == 4) || (et_delta >= 0.0 && et_delta <= 1.0), CVB_ERR_ARG,
+            "early-termination delta must be in [0, 1] (option -a)");
+  const bool prob = et_type == 2 || et_type == 4, cutoff = et_type == 3 || et_type == 4;
+  cudaStream_t st = e->stream;
+  const int64_t nvl = e->nvl;
+  CVB_TRY(cvb_phase_begin(e, 0.0));
+  CVB_TRY(e->et_active.ensure(nvl + 1));
+  CVB_TRY(e->et_frozen_target.ensure(nvl + 1));
+  CVB_TRY(e->et_frozen_cw.ensure(nvl + 1));
+  CVB_TRY(e->et_count.ensure(4));
+  CVB_CUDA(cudaMemsetAsync(e->et_active.p, 1, nvl + 1, st));
+  CVB_CUDA(cudaMemsetAsync(e->et_count.p, 0, 4 * sizeof(unsigned int), st));
+  if (prob) {
+    for (auto &b : e->et_p) CVB_TRY(b.ensure(nvl + 1));
+    if (nvl > 0) {
+      k_fill_f64<<<grid_for(nvl, 256), 256, 0, st>>>(e->et_p[0].p, nvl, 1.0);  // p_prev = 1 (louvain.cpp:250)
+      CVB_CUDA(cudaMemsetAsync(e->et_p[1].p, 0, nvl * sizeof(double), st));
+    }
+  }
+  struct Restore { cvb_engine *e; ~Restore() { e->et_no_deltas = false; } } restore{e};
+  e->et_no_deltas = true;
+  double prev = lower, cur = -1.0;
+  int iters = 0, pp = 0;
+  unsigned int frozen = 0;  // vc_count of the iteration about to run = vertices frozen so far
+  while (true) {
+    iters++;
+    CVB_TRY(cvb_sweep(e));
+    if (nvl > 0)
+      k_et_fix<<<grid_for(nvl, 256), 256, 0, st>>>(nvl, e->et_active.p, e->lab[e->targ].p, e->lab[e->curr].p,
+                                                   e->et_frozen_target.p, e->cw.p, e->et_frozen_cw.p, e->vdeg.p,
+                                                   e->ddeg.p, e->dsize.p);
+    e->launches++;
+    if (cutoff && frozen >= 90u) {  // ET_CUTOFF, louvain.hpp:76; louvain.cpp:114-120
+      // the reference leaves the loop BEFORE distUpdateLocalCinfo: drop this sweep's deltas
+      CVB_CUDA(cudaMemsetAsync(e->ddeg.p, 0, e->nvg * sizeof(double), st));
+      CVB_CUDA(cudaMemsetAsync(e->dsize.p, 0, e->nvg * sizeof(int32_t), st));
+      cur = -1.0;
+      break;
+    }
+    double sums[2];
+    CVB_TRY(cvb_apply_and_reduce(e, sums));
+    cur = cvb_modularity_from_sums(e, sums);
+    if ((cur - prev) < thresh) break;
+    prev = cur;
+    if (prev < lower) prev = lower;
+    if (nvl > 0)
+      k_et_rotate<<<grid_for(nvl, 256), 256, 0, st>>>(nvl, iters, prob ? 1 : 0, 1.0 - et_delta, e->lab[e->past].p,
+                                                      e->lab[e->curr].p, e->lab[e->targ].p, e->et_active.p,
+                                                      e->et_frozen_target.p, prob ? e->et_p[pp].p : nullptr,
+                                                      prob ? e->et_p[pp ^ 1].p : nullptr, e->et_count.p);
+    e->launches++;
+    pp ^= 1;  // std::swap(p_curr, p_prev), louvain.cpp:401
+    CVB_CUDA(cudaMemcpyAsync(&frozen, e->et_count.p, sizeof frozen, cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(cudaStreamSynchronize(st));
+  }
+  if (q_out) *q_out = prev;
+  if (iters_out) *iters_out = iters;
+  return CVB_OK;
+}
+
 int cvb_louvain_run_ex(cvb_engine *e, int max_levels, int flags, double *level_q, int *level_iters,
                        int64_t *level_nv, int64_t *comm_out) {
+  return cvb_louvain_run_et(e, max_levels, flags, 0, 1.0, level_q, level_iters, level_nv, comm_out);
+}
+
+int cvb_louvain_run_et(cvb_engine *e, int max_levels, int flags, int et_type, double et_delta, double *level_q,
+                       int *level_iters, int64_t *level_nv, int64_t *comm_out) {
   if (!e || !e->graph_ready) { set_error("cvb_louvain_run: no graph uploaded"); return CVB_ERR_STATE; }
   if (e->nvl != e->nvg) { set_error("cvb_louvain_run is the one-GPU driver"); return CVB_ERR_STATE; }
   cudaStream_t st = e->stream;
@@ -1962,7 +2038,8 @@ int cvb_louvain_run_ex(cvb_engine *e, int max_levels, int flags, double *level_q
       const int sp = phase % 13;
       threshold = sp <= 2 ? 1.0e-3 : sp <= 6 ? 1.0e-4 : sp <= 9 ? 1.0e-5 : 1.0e-6;
     }
-    int rc = cvb_phase_run(e, curr, threshold, 0, &curr, &iters);  // main.cpp:344
+    int rc = et_type ? cvb_phase_run_et(e, curr, threshold, et_type, et_delta, &curr, &iters)  // main.cpp:326-341
+                     : cvb_phase_run(e, curr, threshold, 0, &curr, &iters);                    // main.cpp:344
     if (rc != CVB_OK) return rc;
     tot_iters += iters;
     if ((curr - prev) > threshold) {  // main.cpp:361
@@ -2135,6 +2212,23 @@ int cvb_dist_phase_begin(cvb_engine *e) {
   if (d.world > 1) {  // community degrees of every vertex: all-gather of the vertex degrees
     CVB_TRY(dist_allgather_rows(e, e->vdeg.p, e->cdeg.p, ncclFloat64, sizeof(double)));
     CVB_CUDA(cudaMemcpyAsync(e->vdeg_global.p, e->cdeg.p, e->nvg * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    // degree-ordered gather layout over the GLOBAL vertices (once per graph): the replicated packed[]
+    // array is as large as the whole graph on every rank, and the partitioned inputs carry permuted
+    // ids — without it the records of the hubs are scattered over all of it
+    if (e->lm_ready && e->use_remap && !e->remap && e->mode == CVB_WEIGHTS_U32) {
+      CVB_TRY(e->rank.ensure(e->nvg + 1));
+      CVB_TRY(e->tails_r.ensure(static_cast<size_t>(e->ne) + 1));
+      CVB_TRY(e->staging2.ensure(64 * sizeof(unsigned int)));
+      unsigned int *hist = reinterpret_cast<unsigned int *>(e->staging2.p);
+      CVB_CUDA(cudaMemsetAsync(hist, 0, 64 * sizeof(unsigned int), st));
+      k_degree_hist<<<grid_for(e->nvg, 256), 256, 0, st>>>(e->vdeg_global.p, e->nvg, hist);
+      k_degree_prefix<<<1, 32, 0, st>>>(hist);
+      k_degree_rank<<<grid_for(e->nvg, 256), 256, 0, st>>>(e->vdeg_global.p, e->nvg, hist, e->rank.p);
+      if (e->ne > 0)
+        k_remap_tails<<<grid_for(e->ne, 256), 256, 0, st>>>(e->tails.p, e->rank.p, e->ne, e->tails_r.p);
+      e->launches += 4;
+      e->remap = true;
+    }
   }
   d.stage_n = 0;
   for (auto &x : d.stage_ms) x = 0.0;

@@ -53,8 +53,9 @@ struct LmParams {
   // degree-class list, biggest classes first) and packed[] is indexed by rank, so the records of the
   // high-degree vertices — the ones most entries point to — are contiguous and stay in L1/L2.  The
   // vertex at class-list position i has rank rank_top - i.
-  int remap;
+  int remap;        // 0 identity, 1 rank = rank_top - list position (one GPU), 2 rank[] lookup (N GPUs)
   int rank_top;
+  const vid_t *__restrict__ rank;  // [nv_global] (remap == 2)
   int simple_rows;  // every row holds each tail at most once (singleton neighbours bypass the table)
   vid_t *__restrict__ target;  // [nv_local]
   double *__restrict__ cw;     // [nv_local]
@@ -64,7 +65,37 @@ struct LmParams {
 
 // index of a vertex's own record in packed[] (and the value its self-loop entries carry in tails[])
 __device__ __forceinline__ uint32_t lm_self(const LmParams &p, uint32_t v, int list_pos) {
-  return p.remap ? static_cast<uint32_t>(p.rank_top - list_pos) : v + static_cast<uint32_t>(p.base);
+  if (p.remap == 1) return static_cast<uint32_t>(p.rank_top - list_pos);
+  const uint32_t g = v + static_cast<uint32_t>(p.base);
+  return p.remap == 2 ? static_cast<uint32_t>(__ldg(&p.rank[g])) : g;
+}
+
+// N GPUs: rank of every GLOBAL vertex by decreasing degree class (floor(log2(degree))), from the replicated
+// vertex degrees.  Counting sort with one atomic cursor per class: the order inside a class is arbitrary
+// (it only decides which cache line a record lives in, never a result).
+__global__ void k_degree_hist(const double *__restrict__ vdeg, int64_t nv, unsigned int *__restrict__ hist) {
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < nv;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const unsigned long long d = static_cast<unsigned long long>(vdeg[v]);
+    atomicAdd(&hist[d ? 63 - __clzll(d) + 1 : 0], 1u);
+  }
+}
+__global__ void k_degree_prefix(unsigned int *__restrict__ hist) {  // 64 classes, descending: hist[c] <- first rank of class c
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned int run = 0;
+  for (int c = 63; c >= 0; --c) {
+    const unsigned int n = hist[c];
+    hist[c] = run;
+    run += n;
+  }
+}
+__global__ void k_degree_rank(const double *__restrict__ vdeg, int64_t nv, unsigned int *__restrict__ cursor,
+                              vid_t *__restrict__ rank) {
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < nv;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const unsigned long long d = static_cast<unsigned long long>(vdeg[v]);
+    rank[v] = static_cast<vid_t>(atomicAdd(&cursor[d ? 63 - __clzll(d) + 1 : 0], 1u));
+  }
 }
 
 // rank[v] = nv-1 - (position of v in the degree-class list): one thread per list position (one GPU: nv_local == nv_global)

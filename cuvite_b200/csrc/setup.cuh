@@ -61,6 +61,12 @@ __global__ void k_convert_edges(const void *__restrict__ aos, const int64_t *__r
 
 __global__ void k_flag_to_f64(const int *__restrict__ flag, double *__restrict__ out) { out[0] = flag[0] ? 1.0 : 0.0; }
 
+__global__ void k_fill_f64(double *__restrict__ dst, int64_t n, double v) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = v;
+}
+
 __global__ void k_fill_u32(uint32_t *__restrict__ dst, int64_t n, uint32_t v) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
@@ -440,6 +446,80 @@ __global__ void __launch_bounds__(kReduceBlock) k_reduce_only(int64_t own0, int6
       out[0] = fe;
       out[1] = fa;
       *ticket = 0;
+    }
+  }
+}
+
+// ---- early termination (options -t 1..4 / -a; louvain.cpp:7-204, 206-423) ------------------
+// After a sweep that ran with the delta atomics switched off: frozen vertices get their frozen
+// target / clusterWeight back (louvain.cpp:97-101: an inactive vertex is skipped, its clusterWeight
+// is the frozen one and it contributes no community update); active vertices record the new
+// clusterWeight as the frozen one (louvain.cpp:107) and contribute their move.
+__global__ void k_et_fix(int64_t nvl, const unsigned char *__restrict__ active, vid_t *__restrict__ target,
+                         const vid_t *__restrict__ curr, const vid_t *__restrict__ frozen_target,
+                         double *__restrict__ cw, double *__restrict__ frozen_cw, const double *__restrict__ vdeg,
+                         double *__restrict__ ddeg, int32_t *__restrict__ dsize) {
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvl;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (!active[v]) {
+      target[v] = frozen_target[v];
+      cw[v] = frozen_cw[v];
+    } else {
+      frozen_cw[v] = cw[v];
+      const vid_t t = target[v], c = curr[v];
+      if (t != c) {
+        const double d = vdeg[v];
+        atomicAdd(&ddeg[t], d);
+        atomicAdd(&dsize[t], 1);
+        atomicAdd(&ddeg[c], -d);
+        atomicAdd(&dsize[c], -1);
+      }
+    }
+  }
+}
+
+// The per-vertex label rotation with the freeze rules, bug for bug:
+//   types 1, 3 (louvain.cpp:174-186): EVERY vertex, frozen or not, either freezes — when
+//     numIters > 2 and `targetComm[i] == currComm[i] == pastComm[i]`, which C++ parses as
+//     (target == curr) == past, a bool compared with a community id — or rotates its labels;
+//   types 2, 4 (louvain.cpp:375-398): a frozen vertex is skipped; an active one whose label did not
+//     change (curr == past, numIters > 2) multiplies its probability by (1 - delta) and freezes at
+//     p <= 0.02 (P_CUTOFF, louvain.hpp:80); active vertices rotate.  p_curr is only written on that
+//     branch and the two arrays are swapped afterwards (louvain.cpp:401), stale values included.
+__global__ void k_et_rotate(int64_t nvl, int num_iters, int prob, double one_minus_delta, vid_t *__restrict__ past,
+                            vid_t *__restrict__ curr, vid_t *__restrict__ target, unsigned char *__restrict__ active,
+                            vid_t *__restrict__ frozen_target, const double *__restrict__ p_prev,
+                            double *__restrict__ p_curr, unsigned int *__restrict__ frozen_count) {
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvl;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    bool rotate;
+    if (!prob) {
+      const bool freeze = num_iters > 2 && (static_cast<vid_t>(target[v] == curr[v]) == past[v]);
+      if (freeze && active[v]) {
+        active[v] = 0;
+        frozen_target[v] = target[v];
+        atomicAdd(frozen_count, 1u);
+      }
+      rotate = !freeze;
+    } else {
+      if (!active[v]) continue;
+      if (num_iters > 2 && curr[v] == past[v]) {
+        const double pc = p_prev[v] * one_minus_delta;
+        p_curr[v] = pc;
+        if (pc <= 0.02) {
+          active[v] = 0;
+          frozen_target[v] = target[v];
+          atomicAdd(frozen_count, 1u);
+        }
+      }
+      rotate = active[v] != 0;
+    }
+    if (rotate) {
+      const vid_t tmp = past[v];
+      past[v] = curr[v];
+      curr[v] = target[v];
+      target[v] = tmp;
+      if (!active[v]) frozen_target[v] = target[v];  // types 1, 3: a frozen vertex that rotates carries its labels along
     }
   }
 }

@@ -211,15 +211,22 @@ class GpuGraph:
         check(self._L.cvb_coarsen(self._h, C.byref(n)), "coarsen")
         return n.value
 
-    def run(self, max_levels: int = 200, threshold_cycling: bool = False):
-        """cvb_louvain_run[_ex]: the phase loop of main.cpp:218-495 (threshold_cycling = option -i)."""
+    def phase_run_et(self, et_type: int, et_delta: float = 1.0, lower: float = -1.0, thresh: float = 1e-6):
+        """cvb_phase_run_et: one phase with early termination (options -t et_type, -a et_delta)."""
+        q, it = C.c_double(0), C.c_int(0)
+        check(self._L.cvb_phase_run_et(self._h, lower, thresh, et_type, et_delta, C.byref(q), C.byref(it)), "phase_run_et")
+        return q.value, it.value
+
+    def run(self, max_levels: int = 200, threshold_cycling: bool = False, et_type: int = 0, et_delta: float = 1.0):
+        """cvb_louvain_run[_ex/_et]: the phase loop of main.cpp:218-495 (threshold_cycling = option -i,
+        et_type / et_delta = options -t / -a)."""
         nv0 = self.info().nv_local
         lq = np.zeros(max_levels)
         li = np.zeros(max_levels, np.int32)
         ln = np.zeros(max_levels, np.int64)
         comm = np.empty(nv0, np.int64)
-        n = self._L.cvb_louvain_run_ex(self._h, max_levels, 1 if threshold_cycling else 0, _ptr(lq), _ptr(li),
-                                       _ptr(ln), _ptr(comm))
+        n = self._L.cvb_louvain_run_et(self._h, max_levels, 1 if threshold_cycling else 0, et_type, et_delta,
+                                       _ptr(lq), _ptr(li), _ptr(ln), _ptr(comm))
         if n < 0:
             check(n, "louvain_run")
         return list(lq[:n]), [int(x) for x in li[:n]], [int(x) for x in ln[:n]], comm

@@ -287,6 +287,17 @@ enum { CVB_RUN_THRESHOLD_CYCLING = 1 };
 int cvb_louvain_run_ex(cvb_engine *e, int max_levels, int flags, double *level_q, int *level_iters,
                        int64_t *level_nv, int64_t *comm_out);
 
+/* Early termination, options -t 1..4 and -a (main.cpp:613-618, 326-341): the phase with per-vertex
+ * freezing — louvain.cpp:7-204 for et_type 1 (local) and 3 (stops once 90 vertices are frozen),
+ * louvain.cpp:206-423 for et_type 2 and 4 (probabilistic: a vertex whose label did not change
+ * multiplies its probability by 1 - et_delta and freezes at p <= 0.02).  The freeze rules are
+ * mirrored bug for bug (see setup.cuh, k_et_rotate).  One GPU. */
+int cvb_phase_run_et(cvb_engine *e, double lower, double thresh, int et_type, double et_delta,
+                     double *q_out, int *iters_out);
+/* cvb_louvain_run_ex with every phase run by cvb_phase_run_et (et_type 0 = no early termination). */
+int cvb_louvain_run_et(cvb_engine *e, int max_levels, int flags, int et_type, double et_delta,
+                       double *level_q, int *level_iters, int64_t *level_nv, int64_t *comm_out);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Kernels launched by this engine since creation (bench.py "gpu_launches"). */
 int64_t cvb_launch_count(const cvb_engine *e);

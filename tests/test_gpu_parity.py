@@ -584,3 +584,36 @@ def test_real_weight_hub_graph_f64_mode_within_tolerance(oracle):
         assert same_labels, "labels differ from the CPU checker (modularity still within 1e-6)"
     finally:
         gpu.close()
+
+
+@pytest.mark.parametrize("graph", ["er3000", "rmat13"])
+@pytest.mark.parametrize("et_type,delta", [(1, 1.0), (3, 1.0), (2, 0.9), (4, 0.9), (2, 0.25), (4, 1.0)])
+def test_early_termination_matches_reference_cli(tmp_path, graph, et_type, delta):
+    """cvb_louvain_run_et == the reference CLI with -t <type> [-a <delta>] (louvain.cpp:7-423, main.cpp:326-341)
+    on graphs where early termination changes the trajectory: Q as printed (6 significant digits) and
+    cumulative iterations per level.  The freeze rules are mirrored bug for bug (k_et_rotate)."""
+    import os
+    import re
+    import subprocess
+    from cuvite_b200 import graphgen as gg, vite_io
+    from cuvite_b200.engine import GpuGraph
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "gc_cpu64")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/gc_cpu64 not built (needs /root/reference at build time)")
+    g = gg.erdos_renyi(3000, 8.0, seed=1) if graph == "er3000" else gg.rmat(13, seed=2)
+    f = str(tmp_path / "h.bin")
+    vite_io.write_vite(f, g)
+    opts = ["-t", str(et_type)] + (["-a", str(delta)] if et_type in (2, 4) else [])
+    r = subprocess.run([exe, "-f", f] + opts, capture_output=True, text=True, timeout=600, cwd=str(tmp_path),
+                       env=dict(os.environ, OMP_NUM_THREADS="4"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    want = re.findall(r"Level \d+, Modularity: ([0-9.eE+-]+), Clustering time: [^,]*, Iterations: (\d+)", r.stdout)
+    assert want
+    gpu = GpuGraph()
+    try:
+        gpu.upload(g.offsets.numpy(), g.tails.numpy(), g.weights.numpy())
+        lq, li, _, _ = gpu.run(et_type=et_type, et_delta=delta)
+    finally:
+        gpu.close()
+    assert [f"{q:.6g}" for q in lq] == [f"{float(q):.6g}" for q, _ in want]
+    assert li == [int(i) for _, i in want]
