@@ -211,6 +211,7 @@ struct cvb_engine {
   DevBuf<vid_t> rank, tails_r;  // degree-ordered gather layout (one GPU): rank[v], tails mapped to ranks
   bool remap = false;          // the sweep reads tails_r / rank-ordered packed[]
   bool use_remap = true;       // CVB_REMAP=0 disables it
+  bool use_hash2 = true;       // CVB_HASH2=0: the round-1 hash kernels (separate key / weight arrays, no unit / singleton paths)
   bool use_lm = true;          // CVB_LM=0: first-generation hash/group kernels only
   uint32_t lm_mask = (1u << kClsG8) | (1u << kClsG16) | (1u << kClsG32) | (1u << kClsH16K);  // classes on lm.cuh
   bool lm_ready = false;       // vrec/selfw built for the current graph (U32 mode, < 2^32 entries)
@@ -227,9 +228,11 @@ struct cvb_engine {
   bool use_first_sweep = true; // cvb env CVB_NO_FIRST_SWEEP=1 disables the singleton fast path
   bool rows_simple = false;    // every row holds each tail at most once (ascending)
   int sweeps_in_phase = 0;     // 0 right after cvb_phase_begin: all vertices are singletons
-  static constexpr int kAux = 4;
-  cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kAux = 12;
+  cudaStream_t aux[kAux] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {};
+  int nstreams = 12;  // streams the class kernels of a sweep are spread over (CVB_STREAMS; r01 used 4)
+  cudaStream_t S(int k) const { return aux[k % nstreams]; }
 
   DistState dist;  // N > 1: NCCL communicator and vertex ranges (dist.cuh)
   // early termination (cvb_phase_run_et)
@@ -356,8 +359,28 @@ int launch_hash_impl(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, co
   return CVB_OK;
 }
 
+template <int TPV, int KC, int NCH, int MINB, bool UNIT>
+int launch_hash2_impl(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const vid_t *list, int64_t n) {
+  constexpr int VPB = TPV <= 32 ? 256 / TPV : 1;
+  constexpr int THREADS = TPV <= 32 ? 256 : TPV;
+  const size_t smem = hash2_block_smem<TPV, KC, NCH>();
+  if (first_use_on_device(e->device, reinterpret_cast<const void *>(&k_sweep_u32_hash2<TPV, KC, NCH, MINB, UNIT>))) {
+    CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_hash2<TPV, KC, NCH, MINB, UNIT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  }
+  int64_t grid = (n + VPB - 1) / VPB;
+  const int64_t cap = static_cast<int64_t>(e->num_sms) * MINB;
+  if (grid > cap) grid = cap;
+  k_sweep_u32_hash2<TPV, KC, NCH, MINB, UNIT><<<static_cast<int>(grid), THREADS, smem, st>>>(p, list, static_cast<int>(n));
+  e->launches++;
+  return CVB_OK;
+}
+
 template <int TPV, int KC, int NCH, int MINB>
 int launch_hash(cvb_engine *e, cudaStream_t st, const SweepU32Params &p, const vid_t *list, int64_t n) {
+  if (e->use_hash2 && !e->use_split && !(TPV >= 128 && e->use_tma))
+    return e->unit_weights ? launch_hash2_impl<TPV, KC, NCH, MINB, true>(e, st, p, list, n)
+                           : launch_hash2_impl<TPV, KC, NCH, MINB, false>(e, st, p, list, n);
   if (e->use_split) return launch_hash_impl<TPV, KC, NCH, MINB, false, true>(e, st, p, list, n);
   if (TPV >= 128 && e->use_tma) return launch_hash_impl<TPV, KC, NCH, MINB, (TPV >= 128)>(e, st, p, list, n);
   return launch_hash_impl<TPV, KC, NCH, MINB, false>(e, st, p, list, n);
@@ -455,7 +478,7 @@ int launch_sweep_u32(cvb_engine *e) {
   cudaStream_t st = e->stream;
   const bool lm = e->use_lm && e->lm_ready;
   const bool first_sweep = e->sweeps_in_phase == 0 && e->rows_simple && e->use_first_sweep;
-  const bool remap = lm && e->remap;
+  const bool remap = lm && e->remap && !e->use_split;  // the split-gather A/B variant indexes labels[] by vertex id
   k_pack_labels<<<grid_for(e->nvg, 256), 256, 0, st>>>(e->nvg, e->sweep_labels(), e->cdeg.p, e->csize.p,
                                                        e->packed.p, remap ? e->rank.p : nullptr);
   e->launches++;
@@ -476,6 +499,7 @@ int launch_sweep_u32(cvb_engine *e) {
   p.labels = e->sweep_labels();
   p.csize = e->csize.p;
   p.cdeg32 = nullptr;
+  p.simple_rows = (e->rows_simple && !getenv("CVB_NO_SINGLETON_SKIP")) ? 1 : 0;
   if (e->use_split) {
     CVB_TRY(e->cdeg32.ensure(e->nvg + 1));
     k_cdeg32<<<grid_for(e->nvg, 256), 256, 0, st>>>(e->nvg, e->cdeg.p, e->cdeg32.p);
@@ -508,7 +532,7 @@ int launch_sweep_u32(cvb_engine *e) {
     // singleton start: nothing to merge, table-free kernels (one launch per width)
     auto span = [&](int c0, int c1) { return e->class_start[c1 + 1] - e->class_start[c0]; };
     CVB_CUDA(cudaEventRecord(e->ev_fork, st));
-    for (int i = 0; i < cvb_engine::kAux; ++i) CVB_CUDA(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
+    for (int i = 0; i < e->nstreams; ++i) CVB_CUDA(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
     auto go = [&](auto kern, int tpv, int c0, int c1, cudaStream_t s2) {
       const int64_t m = span(c0, c1);
       if (m <= 0) return;
@@ -532,18 +556,18 @@ int launch_sweep_u32(cvb_engine *e) {
           kern_w<<<static_cast<int>(grid), threads, 0, s2>>>(q, static_cast<int>(pos(c0)), static_cast<int>(m));
         e->launches++;
       };
-      gof(k_lm_first_block<512, true>, k_lm_first_block<512, false>, 512, 1, kClsH8K, kClsH16K, e->aux[0]);
-      gof(k_lm_first_block<128, true>, k_lm_first_block<128, false>, 128, 1, kClsH2K, kClsH4K, e->aux[0]);
-      gof(k_lm_first_group<32, true>, k_lm_first_group<32, false>, 256, 8, kClsH512, kClsH1K, e->aux[2]);
-      gof(k_lm_first_group<16, true>, k_lm_first_group<16, false>, 256, 16, kClsH256, kClsH256, e->aux[2]);
-      gof(k_lm_first_group<8, true>, k_lm_first_group<8, false>, 256, 32, kClsG32, kClsH128, e->aux[3]);
-      gof(k_lm_first_group<4, true>, k_lm_first_group<4, false>, 256, 64, kClsG8, kClsG16, e->aux[3]);
-      go(k_sweep_u32_first<1>, 1, kClsG4, kClsG4, e->aux[3]);
+      gof(k_lm_first_block<512, true>, k_lm_first_block<512, false>, 512, 1, kClsH8K, kClsH16K, e->S(0));
+      gof(k_lm_first_block<128, true>, k_lm_first_block<128, false>, 128, 1, kClsH2K, kClsH4K, e->S(4));
+      gof(k_lm_first_group<32, true>, k_lm_first_group<32, false>, 256, 8, kClsH512, kClsH1K, e->S(2));
+      gof(k_lm_first_group<16, true>, k_lm_first_group<16, false>, 256, 16, kClsH256, kClsH256, e->S(5));
+      gof(k_lm_first_group<8, true>, k_lm_first_group<8, false>, 256, 32, kClsG32, kClsH128, e->S(3));
+      gof(k_lm_first_group<4, true>, k_lm_first_group<4, false>, 256, 64, kClsG8, kClsG16, e->S(6));
+      go(k_sweep_u32_first<1>, 1, kClsG4, kClsG4, e->S(7));
     } else {
-    go(k_sweep_u32_first<256>, 256, kClsH2K, kClsH16K, e->aux[0]);
-    go(k_sweep_u32_first<32>, 32, kClsH256, kClsH1K, e->aux[2]);
-    go(k_sweep_u32_first<8>, 8, kClsG16, kClsH128, e->aux[3]);
-    go(k_sweep_u32_first<1>, 1, kClsG4, kClsG8, e->aux[3]);
+    go(k_sweep_u32_first<256>, 256, kClsH2K, kClsH16K, e->S(0));
+    go(k_sweep_u32_first<32>, 32, kClsH256, kClsH1K, e->S(2));
+    go(k_sweep_u32_first<8>, 8, kClsG16, kClsH128, e->S(3));
+    go(k_sweep_u32_first<1>, 1, kClsG4, kClsG8, e->S(3));
     }
     if ((n = span(kClsC2, kClsGiant)) > 0) {  // every vertex above 8192 entries: chunked over the grid
       GiantTables gt{};
@@ -552,13 +576,13 @@ int launch_sweep_u32(cvb_engine *e) {
       gt.table_start = e->big_layout.p + (n + 1);
       gt.gmeta = e->big_meta.p;
       int64_t g1 = e->big_chunks < 8LL * e->num_sms ? e->big_chunks : 8LL * e->num_sms;
-      k_sweep_u32_first_giant<<<static_cast<int>(g1), 512, 0, e->aux[1]>>>(p, lst(kClsC2), (int)n, gt, e->big_chunks,
+      k_sweep_u32_first_giant<<<static_cast<int>(g1), 512, 0, e->S(1)>>>(p, lst(kClsC2), (int)n, gt, e->big_chunks,
                                                                           e->gchunk_gain.p, e->gchunk_key.p);
-      k_sweep_u32_first_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(
+      k_sweep_u32_first_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->S(1)>>>(
           p, lst(kClsC2), (int)n, gt, e->gchunk_gain.p, e->gchunk_key.p);
       e->launches += 2;
     }
-    for (int i = 0; i < cvb_engine::kAux; ++i) {
+    for (int i = 0; i < e->nstreams; ++i) {
       CVB_CUDA(cudaEventRecord(e->ev_join[i], e->aux[i]));
       CVB_CUDA(cudaStreamWaitEvent(st, e->ev_join[i], 0));
     }
@@ -566,7 +590,7 @@ int launch_sweep_u32(cvb_engine *e) {
     return CVB_OK;
   }
   CVB_CUDA(cudaEventRecord(e->ev_fork, st));
-  for (int i = 0; i < cvb_engine::kAux; ++i) CVB_CUDA(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
+  for (int i = 0; i < e->nstreams; ++i) CVB_CUDA(cudaStreamWaitEvent(e->aux[i], e->ev_fork, 0));
   // Which generation serves a degree class is decided per class from the measurements of round 2
   // (profiles/r02_*: R-MAT scale 20 and 24): the second-generation kernels (lm.cuh) win on the small
   // classes (5..32 entries: per-vertex records, sub-warp groups without match.any), on 4097..8192 and,
@@ -577,14 +601,14 @@ int launch_sweep_u32(cvb_engine *e) {
   auto on_lm = [&](int c) { return ((lm_mask >> c) & 1u) != 0u; };
   // hash classes: 8 CSR entries per thread, TPV = upper degree / 8 threads per vertex
   // stream 0: block-per-vertex classes, largest vertices first
-  if (on_lm(kClsH16K)) CVB_TRY((launch_lm_block<1024, 14>(e, e->aux[0], q, pos(kClsH16K), cnt(kClsH16K))));
-  else if ((n = cnt(kClsH16K)) > 0) CVB_TRY((launch_hash<1024, 4, 2, 1>(e, e->aux[0], p, lst(kClsH16K), n)));
-  if (on_lm(kClsH8K)) CVB_TRY((launch_lm_block<512, 13>(e, e->aux[0], q, pos(kClsH8K), cnt(kClsH8K))));
-  else if ((n = cnt(kClsH8K)) > 0) CVB_TRY((launch_hash<512, 4, 2, 2>(e, e->aux[0], p, lst(kClsH8K), n)));
-  if (on_lm(kClsH4K)) CVB_TRY((launch_lm_block<256, 12>(e, e->aux[0], q, pos(kClsH4K), cnt(kClsH4K))));
-  else if ((n = cnt(kClsH4K)) > 0) CVB_TRY((launch_hash<256, 4, 2, 4>(e, e->aux[0], p, lst(kClsH4K), n)));
-  if (on_lm(kClsH2K)) CVB_TRY((launch_lm_block<128, 11>(e, e->aux[0], q, pos(kClsH2K), cnt(kClsH2K))));
-  else if ((n = cnt(kClsH2K)) > 0) CVB_TRY((launch_hash<128, 4, 2, 8>(e, e->aux[0], p, lst(kClsH2K), n)));
+  if (on_lm(kClsH16K)) CVB_TRY((launch_lm_block<1024, 14>(e, e->S(0), q, pos(kClsH16K), cnt(kClsH16K))));
+  else if ((n = cnt(kClsH16K)) > 0) CVB_TRY((launch_hash<1024, 4, 2, 1>(e, e->S(0), p, lst(kClsH16K), n)));
+  if (on_lm(kClsH8K)) CVB_TRY((launch_lm_block<512, 13>(e, e->S(4), q, pos(kClsH8K), cnt(kClsH8K))));
+  else if ((n = cnt(kClsH8K)) > 0) CVB_TRY((launch_hash<512, 4, 2, 2>(e, e->S(4), p, lst(kClsH8K), n)));
+  if (on_lm(kClsH4K)) CVB_TRY((launch_lm_block<256, 12>(e, e->S(5), q, pos(kClsH4K), cnt(kClsH4K))));
+  else if ((n = cnt(kClsH4K)) > 0) CVB_TRY((launch_hash<256, 4, 2, 4>(e, e->S(5), p, lst(kClsH4K), n)));
+  if (on_lm(kClsH2K)) CVB_TRY((launch_lm_block<128, 11>(e, e->S(6), q, pos(kClsH2K), cnt(kClsH2K))));
+  else if ((n = cnt(kClsH2K)) > 0) CVB_TRY((launch_hash<128, 4, 2, 8>(e, e->S(6), p, lst(kClsH2K), n)));
   // stream 1: vertices above 8192 entries.  Default: global (L2-resident) tables for all of
   // them; CVB_CLUSTER=1 routes 8193..65536 to thread-block clusters with the table in
   // distributed shared memory (correct, but DSMEM moves ~32 B per 4-byte atomic and
@@ -612,9 +636,9 @@ int launch_sweep_u32(cvb_engine *e) {
     CVB_CHECK(occ1 > 0 && occ2 > 0, CVB_ERR_CUDA, "big-vertex kernels: cannot configure (%s)",
               cudaGetErrorString(cudaGetLastError()));
     const int64_t cap1 = static_cast<int64_t>(e->num_sms) * occ1, cap2 = static_cast<int64_t>(e->num_sms) * occ2;
-    stage<<<static_cast<int>(e->big_chunks < cap1 ? e->big_chunks : cap1), 512, kStageSmem, e->aux[1]>>>(q, bp, e->big_chunks);
-    k_big_pass<<<static_cast<int>(e->bg_items < cap2 ? e->bg_items : cap2), 512, kPassSmem, e->aux[1]>>>(q, bp, e->bg_items);
-    k_big_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(q, bp, static_cast<int>(n));
+    stage<<<static_cast<int>(e->big_chunks < cap1 ? e->big_chunks : cap1), 512, kStageSmem, e->S(1)>>>(q, bp, e->big_chunks);
+    k_big_pass<<<static_cast<int>(e->bg_items < cap2 ? e->bg_items : cap2), 512, kPassSmem, e->S(1)>>>(q, bp, e->bg_items);
+    k_big_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->S(1)>>>(q, bp, static_cast<int>(n));
     e->launches += 3;
   }
   const bool mp = lm && e->mp_ready && !big;
@@ -625,7 +649,7 @@ int launch_sweep_u32(cvb_engine *e) {
       CVB_CHECK(occ > 0, CVB_ERR_CUDA, "lm multipass kernel: cannot configure (%s)",
                 cudaGetErrorString(cudaGetLastError()));
       const int grid = static_cast<int>(n < e->num_sms ? n : e->num_sms);
-      kern<<<grid, 1024, smem, e->aux[1]>>>(q, static_cast<int>(pos(kClsC2)), static_cast<int>(n), e->mp_off.p,
+      kern<<<grid, 1024, smem, e->S(1)>>>(q, static_cast<int>(pos(kClsC2)), static_cast<int>(n), e->mp_off.p,
                                             e->mp_stage.p, e->mp_redo.p);
       e->launches++;
       return CVB_OK;
@@ -638,13 +662,13 @@ int launch_sweep_u32(cvb_engine *e) {
       CVB_CUDA(cudaFuncSetAttribute(k_sweep_u32_twopass, cudaFuncAttributeMaxDynamicSharedMemorySize, kTwoPassSmem));
     }
     const int grid = static_cast<int>(n < e->num_sms ? n : e->num_sms);
-    k_sweep_u32_twopass<<<grid, 1024, kTwoPassSmem, e->aux[1]>>>(p, lst(kClsC2), static_cast<int>(n));
+    k_sweep_u32_twopass<<<grid, 1024, kTwoPassSmem, e->S(1)>>>(p, lst(kClsC2), static_cast<int>(n));
     e->launches++;
   }
   if (e->use_cluster && !mp && !big) {
-    if ((n = cnt(kClsC8)) > 0) CVB_TRY(launch_cluster<8>(e, e->aux[1], p, lst(kClsC8), n));
-    if ((n = cnt(kClsC4)) > 0) CVB_TRY(launch_cluster<4>(e, e->aux[1], p, lst(kClsC4), n));
-    if ((n = cnt(kClsC2)) > 0) CVB_TRY(launch_cluster<2>(e, e->aux[1], p, lst(kClsC2), n));
+    if ((n = cnt(kClsC8)) > 0) CVB_TRY(launch_cluster<8>(e, e->S(1), p, lst(kClsC8), n));
+    if ((n = cnt(kClsC4)) > 0) CVB_TRY(launch_cluster<4>(e, e->S(1), p, lst(kClsC4), n));
+    if ((n = cnt(kClsC2)) > 0) CVB_TRY(launch_cluster<2>(e, e->S(1), p, lst(kClsC2), n));
   }
   if ((n = e->class_start[kClsGiant + 1] - e->class_start[gcls]) > 0) {
     GiantTables gt{};
@@ -672,68 +696,68 @@ int launch_sweep_u32(cvb_engine *e) {
       const int64_t nch = b.chunk_hi - b.chunk_lo, npc = b.piece_hi - b.piece_lo;
       if (e->big_dense) {
         const int64_t g1 = nch < 2LL * e->num_sms ? nch : 2LL * e->num_sms;
-        k_sweep_u32_giant_insert<true><<<static_cast<int>(g1), 512, kGiantSmem, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
+        k_sweep_u32_giant_insert<true><<<static_cast<int>(g1), 512, kGiantSmem, e->S(1)>>>(p, lst(gcls), (int)n, gt,
                                                                                             b.chunk_lo, b.chunk_hi);
         const int64_t g2 = nch < 4LL * e->num_sms ? nch : 4LL * e->num_sms;
-        k_sweep_u32_giant_eval_dense<<<static_cast<int>(g2), 512, 0, e->aux[1]>>>(
+        k_sweep_u32_giant_eval_dense<<<static_cast<int>(g2), 512, 0, e->S(1)>>>(
             p, lst(gcls), (int)n, gt, b.chunk_lo, b.chunk_hi, e->gchunk2_gain.p, e->gchunk2_key.p);
         e->launches += 2;
         continue;
       }
       if (e->giant_direct) {
         const int64_t g0 = nch < 4LL * e->num_sms ? nch : 4LL * e->num_sms;
-        k_sweep_u32_giant_insert_direct<<<static_cast<int>(g0), 512, 0, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
+        k_sweep_u32_giant_insert_direct<<<static_cast<int>(g0), 512, 0, e->S(1)>>>(p, lst(gcls), (int)n, gt,
                                                                                     b.chunk_lo, b.chunk_hi);
       } else {
         const int64_t g1 = nch < 2LL * e->num_sms ? nch : 2LL * e->num_sms;
-        k_sweep_u32_giant_insert<false><<<static_cast<int>(g1), 512, kGiantSmem, e->aux[1]>>>(p, lst(gcls), (int)n, gt,
+        k_sweep_u32_giant_insert<false><<<static_cast<int>(g1), 512, kGiantSmem, e->S(1)>>>(p, lst(gcls), (int)n, gt,
                                                                                              b.chunk_lo, b.chunk_hi);
       }
       const int64_t g2 = npc < 4LL * e->num_sms ? npc : 4LL * e->num_sms;
-      k_sweep_u32_giant_eval<<<static_cast<int>(g2), 512, 0, e->aux[1]>>>(p, lst(gcls), (int)n, gt, b.piece_lo,
+      k_sweep_u32_giant_eval<<<static_cast<int>(g2), 512, 0, e->S(1)>>>(p, lst(gcls), (int)n, gt, b.piece_lo,
                                                                          b.piece_hi);
       e->launches += 2;
     }
     if (e->big_dense) {
-      k_sweep_u32_giant_final_dense<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(
+      k_sweep_u32_giant_final_dense<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->S(1)>>>(
           p, lst(gcls), (int)n, gt, e->gchunk2_gain.p, e->gchunk2_key.p);
       e->launches += 1;
     } else {
-    k_sweep_u32_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->aux[1]>>>(p, lst(gcls), (int)n,
+    k_sweep_u32_giant_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->S(1)>>>(p, lst(gcls), (int)n,
                                                                                          gt);
     e->launches += 1;
     }
   }
   // stream 2: 129..512
-  if (on_lm(kClsH1K)) CVB_TRY((launch_lm_block<64, 10>(e, e->aux[2], q, pos(kClsH1K), cnt(kClsH1K))));
-  else if ((n = cnt(kClsH1K)) > 0) CVB_TRY((launch_hash<64, 4, 2, 16>(e, e->aux[2], p, lst(kClsH1K), n)));
-  if (on_lm(kClsH512)) CVB_TRY((launch_lm_group<32, 8, 9>(e, e->aux[2], q, pos(kClsH512), cnt(kClsH512))));
-  else if ((n = cnt(kClsH512)) > 0) CVB_TRY((launch_hash<32, 4, 2, 4>(e, e->aux[2], p, lst(kClsH512), n)));
+  if (on_lm(kClsH1K)) CVB_TRY((launch_lm_block<64, 10>(e, e->S(2), q, pos(kClsH1K), cnt(kClsH1K))));
+  else if ((n = cnt(kClsH1K)) > 0) CVB_TRY((launch_hash<64, 4, 2, 16>(e, e->S(2), p, lst(kClsH1K), n)));
+  if (on_lm(kClsH512)) CVB_TRY((launch_lm_group<32, 8, 9>(e, e->S(7), q, pos(kClsH512), cnt(kClsH512))));
+  else if ((n = cnt(kClsH512)) > 0) CVB_TRY((launch_hash<32, 4, 2, 4>(e, e->S(7), p, lst(kClsH512), n)));
   // stream 3: 1..128
-  if (on_lm(kClsH256)) CVB_TRY((launch_lm_group<16, 8, 8>(e, e->aux[3], q, pos(kClsH256), cnt(kClsH256))));
-  else if ((n = cnt(kClsH256)) > 0) CVB_TRY((launch_hash<32, 4, 1, 4>(e, e->aux[3], p, lst(kClsH256), n)));
-  if (on_lm(kClsH128)) CVB_TRY((launch_lm_group<8, 8, 7>(e, e->aux[3], q, pos(kClsH128), cnt(kClsH128))));
-  else if ((n = cnt(kClsH128)) > 0) CVB_TRY((launch_hash<32, 2, 1, 4>(e, e->aux[3], p, lst(kClsH128), n)));
-  if (on_lm(kClsG32)) CVB_TRY((launch_lm_group<4, 8, 6>(e, e->aux[3], q, pos(kClsG32), cnt(kClsG32))));
+  if (on_lm(kClsH256)) CVB_TRY((launch_lm_group<16, 8, 8>(e, e->S(3), q, pos(kClsH256), cnt(kClsH256))));
+  else if ((n = cnt(kClsH256)) > 0) CVB_TRY((launch_hash<32, 4, 1, 4>(e, e->S(3), p, lst(kClsH256), n)));
+  if (on_lm(kClsH128)) CVB_TRY((launch_lm_group<8, 8, 7>(e, e->S(8), q, pos(kClsH128), cnt(kClsH128))));
+  else if ((n = cnt(kClsH128)) > 0) CVB_TRY((launch_hash<32, 2, 1, 4>(e, e->S(8), p, lst(kClsH128), n)));
+  if (on_lm(kClsG32)) CVB_TRY((launch_lm_group<4, 8, 6>(e, e->S(9), q, pos(kClsG32), cnt(kClsG32))));
   else if ((n = cnt(kClsG32)) > 0) {
-    k_sweep_u32_group<32><<<static_cast<int>((n * 32 + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG32), (int)n);
+    k_sweep_u32_group<32><<<static_cast<int>((n * 32 + 255) / 256), 256, 0, e->S(9)>>>(p, lst(kClsG32), (int)n);
     e->launches++;
   }
-  if (on_lm(kClsG16)) CVB_TRY((launch_lm_group<4, 4, 5>(e, e->aux[3], q, pos(kClsG16), cnt(kClsG16))));
+  if (on_lm(kClsG16)) CVB_TRY((launch_lm_group<4, 4, 5>(e, e->S(10), q, pos(kClsG16), cnt(kClsG16))));
   else if ((n = cnt(kClsG16)) > 0) {
-    k_sweep_u32_group<16><<<static_cast<int>((n * 16 + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG16), (int)n);
+    k_sweep_u32_group<16><<<static_cast<int>((n * 16 + 255) / 256), 256, 0, e->S(10)>>>(p, lst(kClsG16), (int)n);
     e->launches++;
   }
-  if (on_lm(kClsG8)) CVB_TRY((launch_lm_group<2, 4, 4>(e, e->aux[3], q, pos(kClsG8), cnt(kClsG8))));
+  if (on_lm(kClsG8)) CVB_TRY((launch_lm_group<2, 4, 4>(e, e->S(11), q, pos(kClsG8), cnt(kClsG8))));
   else if ((n = cnt(kClsG8)) > 0) {
-    k_sweep_u32_group<8><<<static_cast<int>((n * 8 + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG8), (int)n);
+    k_sweep_u32_group<8><<<static_cast<int>((n * 8 + 255) / 256), 256, 0, e->S(11)>>>(p, lst(kClsG8), (int)n);
     e->launches++;
   }
   if ((n = cnt(kClsG4)) > 0) {
-    k_sweep_u32_t4<<<static_cast<int>((n + 255) / 256), 256, 0, e->aux[3]>>>(p, lst(kClsG4), (int)n);
+    k_sweep_u32_t4<<<static_cast<int>((n + 255) / 256), 256, 0, e->S(9)>>>(p, lst(kClsG4), (int)n);
     e->launches++;
   }
-  for (int i = 0; i < cvb_engine::kAux; ++i) {
+  for (int i = 0; i < e->nstreams; ++i) {
     CVB_CUDA(cudaEventRecord(e->ev_join[i], e->aux[i]));
     CVB_CUDA(cudaStreamWaitEvent(st, e->ev_join[i], 0));
   }
@@ -1120,6 +1144,11 @@ cvb_engine *cvb_create(void *stream) {
   if (const char *s = getenv("CVB_L2_PERSIST")) e->l2_persist = (s[0] == '1');
   if (const char *s = getenv("CVB_SPLIT")) e->use_split = (s[0] == '1');
   if (const char *s = getenv("CVB_LM")) e->use_lm = (s[0] != '0');
+  if (const char *s = getenv("CVB_HASH2")) e->use_hash2 = (s[0] != '0');
+  if (const char *s = getenv("CVB_STREAMS")) {
+    const int k = atoi(s);
+    if (k >= 1 && k <= cvb_engine::kAux) e->nstreams = k;
+  }
   if (const char *s = getenv("CVB_LM_MASK")) e->lm_mask = static_cast<uint32_t>(strtoul(s, nullptr, 0));
   if (const char *s = getenv("CVB_REMAP")) e->use_remap = (s[0] != '0');
   if (const char *s = getenv("CVB_MP")) e->use_mp = (s[0] == '1');
@@ -1203,7 +1232,24 @@ static int upload_narrowed(cvb_engine *e, const void *edges_aos, const int64_t *
     const unsigned hw = std::thread::hardware_concurrency();
     return static_cast<int>(hw >= 32 ? 16 : (hw >= 4 ? hw / 2 : 1));
   }();
-  if (ne < (1 << 20) || getenv("CVB_NO_NARROW_UPLOAD")) return 0;
+  // Measured on the B200 host (round 2): from PINNED memory the plain 16-byte-per-entry DMA (~50 GB/s)
+  // beats narrowing on the host cores, so the narrow path is taken for pageable sources only (what the
+  // reference's std::vector storage is), where the driver would otherwise stage the copy through its own
+  // bounce buffers.  CVB_NARROW_UPLOAD=1 / 0 forces it on / off.
+  if (ne < (1 << 20)) return 0;
+  {
+    const char *s = getenv("CVB_NARROW_UPLOAD");
+    bool want;
+    if (s && (s[0] == '0' || s[0] == '1')) {
+      want = s[0] == '1';
+    } else {
+      cudaPointerAttributes at{};
+      const void *src = edges_aos ? edges_aos : static_cast<const void *>(tails);
+      want = !(cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost);
+      cudaGetLastError();
+    }
+    if (!want) return 0;
+  }
   if (e->h_stage.ensure(static_cast<size_t>(ne) * 8 + 64) != CVB_OK) { cudaGetLastError(); return 0; }
   if (e->tails.ensure(static_cast<size_t>(ne) + 1) != CVB_OK) return 0;
   int32_t *ht = reinterpret_cast<int32_t *>(e->h_stage.p);

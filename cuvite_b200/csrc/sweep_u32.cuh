@@ -48,6 +48,7 @@ struct SweepU32Params {
   const int32_t *__restrict__ csize;     // [nv_global]
   // degree-ordered gather layout (lm.cuh): packed[] is indexed by rank[global id] and `tails` holds ranks
   const vid_t *__restrict__ rank;        // [nv_global] or nullptr (identity)
+  int simple_rows;                       // every row holds each tail at most once (singleton neighbours bypass the table)
 };
 
 // index of local vertex v's own record in packed[] (and the value its self-loop entries carry in tails[])
@@ -652,6 +653,229 @@ __global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
             wid = red_id[i];
           }
         commit_vertex_u32(p, v, me.x, wg, winner_with_singleton_bit<SPLIT>(p, me.x, wid, wg), vd, counter0);
+        meta[1] = 0u;
+        meta[2] = 0u;
+      }
+      __syncthreads();
+    }
+    hc = hn;
+    v_next = v_next2;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k_sweep_u32_hash2 — the round-2 revision of k_sweep_u32_hash (same work decomposition: K = KC*NCH
+// register-resident claims per thread, two-deep header pipeline), cut where the round-2 profiles put the
+// time: the L1TEX pipe (random gathers + random shared-memory accesses), not the issue slots.
+//   * slots are interleaved {key, weight} 8-byte records: the evaluation frees a slot with ONE
+//     st.shared.v2 instead of two stores;
+//   * UNIT (every weight of the graph is 1): the weights array is never read, and a lane that opens a
+//     slot adds nothing to it — the weight word only counts LATER entries of the same community
+//     (total = 1 + count), so the common case is one CAS + one LDS + one STS per entry;
+//   * on graphs whose rows hold each tail once (p.simple_rows), a neighbour whose community is a
+//     singleton cannot share it with another entry of the row: it bypasses the table and is evaluated
+//     with its own weight.
+// Per table: CAP slots of 8 bytes, then meta[4] = {-, selfloop, counter0, -} for TPV > 32.
+// ---------------------------------------------------------------------------
+template <int TPV, int KC, int NCH>
+__host__ __device__ constexpr size_t hash2_block_smem() {
+  return (TPV <= 32) ? static_cast<size_t>(256 / TPV) * (2 * KC * NCH * TPV) * 8
+                     : static_cast<size_t>(2 * KC * NCH * TPV) * 8 + 16;
+}
+
+__device__ __forceinline__ void sts64_u32(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+template <int TPV, int KC, int NCH, int MINB, bool UNIT>
+__global__ void __launch_bounds__((TPV <= 32 ? 256 : TPV), MINB)
+    k_sweep_u32_hash2(SweepU32Params p, const vid_t *__restrict__ list, int n) {
+  extern __shared__ __align__(16) uint32_t smem_u32[];
+  __shared__ double red_g[32];
+  __shared__ uint32_t red_id[32];
+  constexpr int kWarpsPerVertex = TPV / 32;
+  constexpr int K = KC * NCH;
+  constexpr int CAP = 2 * K * TPV;  // slots per vertex (power of two)
+  constexpr int VPB = TPV <= 32 ? 256 / TPV : 1;
+  constexpr int GL = TPV < 32 ? TPV : 32;  // lanes of one vertex inside a warp
+  constexpr int kWords = CAP * 2 + (TPV > 32 ? 4 : 0);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned gmask = (GL == 32) ? 0xffffffffu : (((1u << GL) - 1u) << (lane & ~static_cast<unsigned>(GL - 1)));
+  const int tid = (TPV <= 32) ? static_cast<int>(threadIdx.x & (TPV - 1)) : static_cast<int>(threadIdx.x);
+  const int vslot = (TPV <= 32) ? static_cast<int>(threadIdx.x / TPV) : 0;
+  const int wiv = (TPV <= 32) ? 0 : static_cast<int>(threadIdx.x >> 5);  // warp in vertex
+  uint32_t *slots = smem_u32 + kWords * vslot;
+  uint32_t *meta = slots + 2 * CAP;  // only for TPV > 32
+  const uint32_t kaddr = smem_addr(slots);
+  for (int s = tid; s < CAP; s += TPV) {
+    slots[2 * s] = kEmptyKeyU;
+    slots[2 * s + 1] = 0u;
+  }
+  if (TPV > 32) {
+    if (tid < 4) meta[tid] = 0u;
+    __syncthreads();
+  } else {
+    __syncwarp(gmask);
+  }
+  const bool bypass = p.simple_rows != 0;
+
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * VPB;
+  int64_t item = static_cast<int64_t>(blockIdx.x) * VPB + vslot;
+  if (item >= n) return;  // all lanes of a vertex leave together
+  VertexHeader hc = fetch_header(p, list[item]);
+  vid_t v_next = (item + stride < n) ? list[item + stride] : -1;
+  for (; item < n; item += stride) {
+    VertexHeader hn = hc;
+    if (v_next >= 0) hn = fetch_header(p, v_next);
+    const vid_t v_next2 = (item + 2 * stride < n) ? list[item + 2 * stride] : -1;
+
+    const vid_t v = hc.v;
+    const eid_t e0 = hc.e0, e1 = hc.e1;
+    const int deg = static_cast<int>(e1 - e0);
+    const vid_t self = self_of(p, v);
+    const uint2 me = hc.me;
+    const uint32_t cc = me.x & kLabelMask;
+    const double vd = hc.vd;
+    int log2cap = 32 - __clz(2 * deg - 1);  // ceil(log2(2*deg)): load factor <= 0.5
+    log2cap = log2cap < 4 ? 4 : (log2cap > 31 - __clz(CAP) ? 31 - __clz(CAP) : log2cap);
+    const uint32_t maskb = ((1u << log2cap) - 1u) << 3;
+
+    const vid_t *__restrict__ row_tails = p.tails + e0;
+    const uint32_t *__restrict__ row_weights = p.weights + e0;
+    // claims of this lane: key, community degree and slot of every entry that opened a table slot
+    // (freshmask) or bypassed the table (directmask)
+    uint32_t ckey[K], cay[K], cw_[K];
+    uint16_t cslot[K];
+    uint32_t freshmask = 0u, directmask = 0u, ownsum = 0u, selfsum = 0u;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t key[KC], w[KC], slb[KC], old[KC];
+      vid_t tail[KC];
+      uint32_t validm = 0u;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int i = tid + (c * KC + k) * TPV;  // 32-bit position inside the row
+        tail[k] = self;  // a safe address for the gather of idle lanes
+        w[k] = UNIT ? 1u : 0u;
+        if (i < deg) {
+          tail[k] = __ldcs(&row_tails[i]);
+          if (!UNIT) w[k] = __ldcs(&row_weights[i]);
+          validm |= 1u << k;
+        }
+      }
+      uint32_t active = 0u;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const bool valid = (validm >> k) & 1u;
+        const uint2 pk = p.packed[tail[k]];
+        key[k] = valid ? pk.x : kEmptyKeyU;
+        cay[c * KC + k] = pk.y;
+        cw_[c * KC + k] = w[k];
+        const bool own = (key[k] & kLabelMask) == cc;  // idle lanes: 0x7fffffff is never a label
+        ownsum += (valid && own) ? w[k] : 0u;
+        selfsum += (valid && tail[k] == self) ? w[k] : 0u;
+        const bool direct = bypass && valid && !own && (pk.x & kSingletonBit);
+        directmask |= direct ? (1u << (c * KC + k)) : 0u;
+        active |= (valid && !own && !direct) ? (1u << k) : 0u;
+      }
+      // first probes of the chunk back to back, collided entries walk their own short loops (double hashing)
+      uint32_t fresh = 0u, pend = 0u;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        slb[k] = hash_key(key[k], log2cap) << 3;
+        old[k] = atoms_cas_if((active >> k) & 1u, kaddr + slb[k], kEmptyKeyU, key[k], key[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const bool act = (active >> k) & 1u;
+        fresh |= (act && old[k] == kEmptyKeyU) ? (1u << k) : 0u;
+        pend |= (act && old[k] != kEmptyKeyU && old[k] != key[k]) ? (1u << k) : 0u;
+      }
+      if (pend) {
+#pragma unroll
+        for (int k = 0; k < KC; ++k)
+          if (pend & (1u << k)) {
+            const uint32_t step = hash_step(key[k], log2cap) << 3;
+            while (true) {
+              slb[k] = (slb[k] + step) & maskb;
+              const uint32_t o = atoms_cas(kaddr + slb[k], kEmptyKeyU, key[k]);
+              if (o == kEmptyKeyU) {
+                fresh |= 1u << k;
+                break;
+              }
+              if (o == key[k]) break;
+            }
+          }
+      }
+      // unit weights: the slot counts the entries AFTER the claim; weighted: every entry adds
+#pragma unroll
+      for (int k = 0; k < KC; ++k)
+        reds_add_if(((active >> k) & 1u) && !(UNIT && ((fresh >> k) & 1u)), kaddr + slb[k] + 4u, w[k]);
+      freshmask |= fresh << (c * KC);
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        ckey[c * KC + k] = key[k];
+        cslot[c * KC + k] = static_cast<uint16_t>(slb[k] >> 3);
+      }
+    }
+    // own-community weight and self-loop weight of the vertex
+    uint32_t c0u = ownsum, slu = selfsum;
+    if (TPV > 1) {
+      c0u = group_sum<GL>(ownsum, gmask);
+      slu = group_sum<GL>(selfsum, gmask);
+    }
+    if (TPV > 32) {
+      if (lane == 0) {
+        if (c0u) atomicAdd(&meta[2], c0u);
+        if (slu) atomicAdd(&meta[1], slu);
+      }
+      __syncthreads();
+      c0u = meta[2];
+      slu = meta[1];
+    } else {
+      __syncwarp(gmask);
+    }
+
+    // ---- evaluate: the claimer of each key reads its total and frees the slot ----
+    const double counter0 = u32_to_f64(c0u);
+    const double eix = counter0 - u32_to_f64(slu);
+    const double ax = u32_to_f64(me.y) - vd;
+    double g = -1.0;
+    uint32_t id = kLabelMask;
+#pragma unroll
+    for (int q = 0; q < K; ++q)
+      if ((freshmask | directmask) & (1u << q)) {
+        uint32_t tot = cw_[q];
+        if (freshmask & (1u << q)) {
+          const uint32_t a = kaddr + (static_cast<uint32_t>(cslot[q]) << 3);
+          tot = lds_u32(a + 4u) + (UNIT ? 1u : 0u);
+          sts64_u32(a, kEmptyKeyU, 0u);
+        }
+        const double g2 = modularity_gain(u32_to_f64(tot), eix, vd, u32_to_f64(cay[q]), ax, p.constant);
+        if (better_u(g2, ckey[q], g, id)) {
+          g = g2;
+          id = ckey[q];
+        }
+      }
+    double wg = g;
+    uint32_t wid = id;
+    if (TPV > 1) wid = group_argmax<GL>(g, id, &wg, gmask);
+    if (TPV <= 32) {
+      if (tid == 0) commit_vertex_u32(p, v, me.x, wg, wid, vd, counter0);
+      __syncwarp(gmask);
+    } else {
+      if (lane == 0) {
+        red_g[wiv] = wg;
+        red_id[wiv] = wid;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int i = 1; i < kWarpsPerVertex; ++i)
+          if (better_u(red_g[i], red_id[i], wg, wid)) {
+            wg = red_g[i];
+            wid = red_id[i];
+          }
+        commit_vertex_u32(p, v, me.x, wg, wid, vd, counter0);
         meta[1] = 0u;
         meta[2] = 0u;
       }
