@@ -37,6 +37,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     if not os.path.exists(NVCC):
         if os.path.exists(OUT):
+            if not (os.path.exists(STAMP) and open(STAMP).read() == dig):
+                sys.stderr.write("cuvite_b200.build: WARNING: no nvcc here and libcuvite_b200.so does not match the "
+                                 "current sources (stale binary in use)\n")
             return OUT  # GPU box without nvcc: use the shipped binary
         raise RuntimeError("nvcc not found and no prebuilt libcuvite_b200.so")
     cmd = [NVCC, *FLAGS, *[os.path.join(CSRC, s) for s in SOURCES], "-o", OUT]

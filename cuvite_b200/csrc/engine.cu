@@ -1520,8 +1520,8 @@ int cvb_phase_run(cvb_engine *e, double lower, double thresh, int max_iters, dou
     if ((cur - prev) < thresh) break;
     prev = cur;
     if (prev < lower) prev = lower;
+    CVB_TRY(cvb_rotate_labels(e));  // also on the max_iters exit: the returned Q belongs to the labels in LABELS_PAST
     if (max_iters > 0 && iters >= max_iters) break;
-    CVB_TRY(cvb_rotate_labels(e));
   }
   if (q_out) *q_out = prev;
   if (iters_out) *iters_out = iters;
@@ -2114,7 +2114,7 @@ int cvb_louvain_run_et(cvb_engine *e, int max_levels, int flags, int et_type, do
     wide.release();
     if (err != cudaSuccess) { set_error("cvb_louvain_run: D2H failed: %s", cudaGetErrorString(err)); return CVB_ERR_CUDA; }
   }
-  return phase;
+  return phase < max_levels ? phase : max_levels;  // the level arrays hold max_levels entries
 }
 
 // ---------------------------------------------------------------------------
@@ -2331,8 +2331,8 @@ int cvb_dist_phase_run(cvb_engine *e, double lower, double thresh, int max_iters
     if ((cur - prev) < thresh) break;
     prev = cur;
     if (prev < lower) prev = lower;
-    if (max_iters > 0 && iters >= max_iters) break;
     CVB_TRY(cvb_dist_advance(e));
+    if (max_iters > 0 && iters >= max_iters) break;
   }
   if (q_out) *q_out = prev;
   if (iters_out) *iters_out = iters;

@@ -5,8 +5,11 @@
 // Layout (64-bit build, little endian, no padding; distgraph.cpp:99-100,131,170):
 //   int64 nv; int64 ne; int64 offsets[nv + 1]; struct { int64 tail; double weight; } edges[ne];
 // ne counts directed CSR entries.
+#include <sys/stat.h>
+
 #include <cstdio>
 #include <cstdlib>
+#include <new>
 #include <vector>
 
 #include "common.cuh"
@@ -57,9 +60,21 @@ int cvb_vite_partition(const char *path, int rank, int nparts, int balanced, cvb
   CVB_CHECK(read_at(fh.f, 0, hdr, sizeof hdr) && hdr[0] >= 0 && hdr[1] >= 0, CVB_ERR_ARG,
             "cvb_vite_partition: %s is not a Vite file (short header)", path);
   const int64_t nv = hdr[0], ne = hdr[1];
+  // the header must describe the file: a corrupt nv / ne would otherwise size host allocations
+  struct stat sb;
+  CVB_CHECK(fstat(fileno(fh.f), &sb) == 0, CVB_ERR_ARG, "cvb_vite_partition: cannot stat %s", path);
+  const __int128 need = static_cast<__int128>(16) + (static_cast<__int128>(nv) + 1) * 8 + static_cast<__int128>(ne) * 16;
+  CVB_CHECK(need <= static_cast<__int128>(sb.st_size), CVB_ERR_ARG,
+            "cvb_vite_partition: %s: header says nv=%lld ne=%lld but the file has only %lld bytes", path,
+            (long long)nv, (long long)ne, (long long)sb.st_size);
   std::vector<int64_t> parts(nparts + 1);
   if (balanced) {  // option -b
-    std::vector<int64_t> seen(nv > 0 ? nv : 1);
+    std::vector<int64_t> seen;
+    try {
+      seen.resize(nv > 0 ? nv : 1);
+    } catch (const std::bad_alloc &) {
+      CVB_CHECK(false, CVB_ERR_ARG, "cvb_vite_partition: %s: cannot allocate %lld offsets", path, (long long)nv);
+    }
     CVB_CHECK(read_at(fh.f, 16, seen.data(), static_cast<size_t>(nv) * 8), CVB_ERR_ARG,
               "cvb_vite_partition: %s: truncated offsets", path);
     balanced_parts(seen, nv, ne, nparts, parts.data());

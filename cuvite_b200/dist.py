@@ -202,9 +202,9 @@ class DistLouvain:
             if (cur - prev) < thresh:
                 break
             prev = max(cur, lower)
+            self.advance()  # also on the max_iters exit: the returned Q belongs to the past labels
             if max_iters and iters >= max_iters:
                 break
-            self.advance()
         return prev, iters
 
 

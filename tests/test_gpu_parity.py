@@ -303,25 +303,44 @@ def test_tma_staged_variant_matches_reference(monkeypatch):
     gpu.close()
 
 
+@pytest.mark.parametrize("big,mp,lm_mask", [("1", "0", None), ("1", "0", "0x1ffc"), ("0", "1", None)])
+def test_big_vertex_paths_match_oracle(oracle, big, mp, lm_mask, monkeypatch):
+    """Round-2 paths for vertices above 8192 entries on the hub graph below (one vertex above 65536 entries):
+    the default partition-then-hash path (k_big_stage / k_big_pass / k_big_final), the same with every class
+    on the second-generation kernels (CVB_LM_MASK=0x1ffc), and the serial multi-pass kernel (CVB_BIG=0
+    CVB_MP=1) with the round-1 global tables above 65536."""
+    monkeypatch.setenv("CVB_BIG", big)
+    monkeypatch.setenv("CVB_MP", mp)
+    if lm_mask:
+        monkeypatch.setenv("CVB_LM_MASK", lm_mask)
+    _giant_hub_case(oracle)
+
+
 @pytest.mark.parametrize("cluster,arena_mb,twopass,dense", [(False, 0, True, True), (True, 0, True, True),
                                                             (False, 1, True, False), (False, 0, False, False),
                                                             (False, 0, False, True)])
 def test_true_giant_hub_matches_oracle(oracle, cluster, arena_mb, twopass, dense, monkeypatch):
-    """Vertices above 8192 entries: the two-pass shared-memory kernel for 8193..16384 (default;
+    """ROUND-1 A/B variants (CVB_BIG=0: the partition-then-hash path off).
+    Vertices above 8192 entries: the two-pass shared-memory kernel for 8193..16384 (default;
     twopass=False sends that class through the global tables too), the global-table path above
     (arena_mb=1 forces one batch per big vertex through the shared table arena) and the
     thread-block-cluster / distributed-shared-memory path (CVB_CLUSTER=1), incl. one vertex
     above 65536 entries.  dense=True (default): the vertices above 16384 entries accumulate into
     dense per-vertex arrays with L2 reductions; dense=False: open-addressing tables in global
     memory."""
-    import torch
-    from cuvite_b200 import graphgen as gg
-    from cuvite_b200.engine import GpuGraph
+    monkeypatch.setenv("CVB_BIG", "0")
     monkeypatch.setenv("CVB_CLUSTER", "1" if cluster else "0")
     monkeypatch.setenv("CVB_NO_TWOPASS", "0" if twopass else "1")
     monkeypatch.setenv("CVB_BIG_DENSE", "1" if dense else "0")
     if arena_mb:
         monkeypatch.setenv("CVB_GIANT_ARENA_MB", str(arena_mb))
+    _giant_hub_case(oracle)
+
+
+def _giant_hub_case(oracle):
+    import torch
+    from cuvite_b200 import graphgen as gg
+    from cuvite_b200.engine import GpuGraph
     gpu = GpuGraph()
     nv = 90000
     bg = gg.erdos_renyi(nv, 6.0, seed=11)
@@ -617,3 +636,16 @@ def test_early_termination_matches_reference_cli(tmp_path, graph, et_type, delta
         gpu.close()
     assert [f"{q:.6g}" for q in lq] == [f"{float(q):.6g}" for q, _ in want]
     assert li == [int(i) for _, i in want]
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_phase_run_max_iters_returns_matching_labels(gpu, k):
+    """on the max_iters exit the returned modularity (iteration k's) must belong to the labels in
+    LABELS_PAST — the input of iteration k, i.e. iteration k-1's targets."""
+    g = load_golden("rmat10_intw")
+    assert int(g["iters"]) > k
+    gpu.upload(*_csr(g))
+    q, iters = gpu.phase_run(max_iters=k)
+    assert iters == k and q == g["qs"][k - 1]
+    want = g["targets"][k - 2] if k >= 2 else np.arange(g["offsets"].size - 1)
+    assert np.array_equal(gpu.labels(0), want)
