@@ -499,7 +499,9 @@ int launch_sweep_u32(cvb_engine *e) {
   p.labels = e->sweep_labels();
   p.csize = e->csize.p;
   p.cdeg32 = nullptr;
-  p.simple_rows = (e->rows_simple && !getenv("CVB_NO_SINGLETON_SKIP")) ? 1 : 0;
+  // singleton bypass: needs community sizes that agree with the labels; early termination rotates the labels of
+  // frozen vertices WITHOUT updating the community info (louvain.cpp:174-186, mirrored), so it is off there
+  p.simple_rows = (e->rows_simple && !e->et_no_deltas && !getenv("CVB_NO_SINGLETON_SKIP")) ? 1 : 0;
   if (e->use_split) {
     CVB_TRY(e->cdeg32.ensure(e->nvg + 1));
     k_cdeg32<<<grid_for(e->nvg, 256), 256, 0, st>>>(e->nvg, e->cdeg.p, e->cdeg32.p);
@@ -516,7 +518,7 @@ int launch_sweep_u32(cvb_engine *e) {
     q.remap = remap ? (e->nvl == e->nvg ? 1 : 2) : 0;
     q.rank = e->rank.p;
     q.rank_top = static_cast<int>(e->nvl - 1);
-    q.simple_rows = (e->rows_simple && !getenv("CVB_NO_SINGLETON_SKIP")) ? 1 : 0;
+    q.simple_rows = p.simple_rows;
     q.weights = reinterpret_cast<const uint32_t *>(e->weights.p);
     q.packed = e->packed.p;
     q.selfw = e->has_selfloops ? e->selfw.p : nullptr;

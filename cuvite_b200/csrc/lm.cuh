@@ -1314,7 +1314,7 @@ __device__ __forceinline__ void lm_first_row(const LmParams &p, const vid_t *__r
                                              const uint32_t *__restrict__ wrow, int lane_pos, int deg, uint32_t self,
                                              double vd, double ax, double &g, uint32_t &id) {
   int i = lane_pos;
-  for (; i + 3 * STRIDE < deg; i += 4 * STRIDE)
+  for (; i + 3 * STRIDE < deg; i += 4 * STRIDE)  // four gathers in flight per lane (eight measured slower: 0.157 vs 0.139 ms)
     lm_first_entries<4, STRIDE, UNIT>(p, row + i, wrow + i, self, vd, ax, g, id);
   if (i + STRIDE < deg) {
     lm_first_entries<2, STRIDE, UNIT>(p, row + i, wrow + i, self, vd, ax, g, id);

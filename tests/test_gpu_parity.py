@@ -623,8 +623,11 @@ def test_early_termination_matches_reference_cli(tmp_path, graph, et_type, delta
     f = str(tmp_path / "h.bin")
     vite_io.write_vite(f, g)
     opts = ["-t", str(et_type)] + (["-a", str(delta)] if et_type in (2, 4) else [])
+    # ONE host thread: the reference keeps vActive in a std::vector<bool> and clears bits of the same word from
+    # several OpenMP threads (louvain.cpp:174-186, 375-398) — with more than one thread freezes get lost and its
+    # own output changes from run to run (observed: three different level-5 modularities in three runs)
     r = subprocess.run([exe, "-f", f] + opts, capture_output=True, text=True, timeout=600, cwd=str(tmp_path),
-                       env=dict(os.environ, OMP_NUM_THREADS="4"))
+                       env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     want = re.findall(r"Level \d+, Modularity: ([0-9.eE+-]+), Clustering time: [^,]*, Iterations: (\d+)", r.stdout)
     assert want
