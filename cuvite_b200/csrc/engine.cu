@@ -235,6 +235,17 @@ struct cvb_engine {
   cudaStream_t S(int k) const { return aux[k % nstreams]; }
 
   DistState dist;  // N > 1: NCCL communicator and vertex ranges (dist.cuh)
+  // colouring (cvb_phase_run_color): per-colour class lists; ovr_* redirect the sweep's class ranges
+  DevBuf<int32_t> col_color, col_keys, col_keys2;
+  DevBuf<vid_t> col_list, col_ids;
+  DevBuf<VertexRec> col_vrec;
+  DevBuf<vid_t> col_bak_t;
+  DevBuf<double> col_bak_cw;
+  int col_num = 0;                       // numColor passed to the Louvain loop (= colours + 1)
+  std::vector<int64_t> col_start;        // [col_num * kNumClasses + 1] start of every (colour, class) range in col_list
+  bool ovr = false;                      // a colour step: classes below kClsC2 come from col_list / col_vrec
+  bool ovr_big = false;                  // ... and this colour has vertices above 8192 entries
+  int ovr_color = 0;
   // early termination (cvb_phase_run_et)
   bool et_no_deltas = false;
   DevBuf<unsigned char> et_active;
@@ -306,8 +317,11 @@ int launch_sweep(cvb_engine *e) {
   p.cw = e->cw.p;
   p.ddeg = (e->labels_only || e->et_no_deltas) ? nullptr : e->ddeg.p;
   p.dsize = (e->labels_only || e->et_no_deltas) ? nullptr : e->dsize.p;
-  auto cnt = [&](int c) { return e->class_start[c + 1] - e->class_start[c]; };
-  auto lst = [&](int c) { return e->list.p + e->class_start[c]; };
+  // (colour steps: the (colour, class) ranges of the per-colour lists — every kernel here takes a list)
+  const int64_t *cs = e->ovr ? e->col_start.data() + static_cast<size_t>(e->ovr_color) * kNumClasses : e->class_start;
+  const vid_t *cl = e->ovr ? e->col_list.p : e->list.p;
+  auto cnt = [&](int c) { return cs[c + 1] - cs[c]; };
+  auto lst = [&](int c) { return cl + cs[c]; };
   int64_t n;
   if ((n = cnt(kClsG4)) > 0) {
     k_sweep_group<4, W><<<static_cast<int>((n * 4 + 255) / 256), 256, 0, e->stream>>>(p, lst(kClsG4), (int)n);
@@ -326,12 +340,12 @@ int launch_sweep(cvb_engine *e) {
     e->launches++;
   }
   // adjacent classes are contiguous in the list, so two classes go out in one launch
-  auto cnt2 = [&](int c) { return e->class_start[c + 2] - e->class_start[c]; };
+  auto cnt2 = [&](int c) { return cs[c + 2] - cs[c]; };
   if ((n = cnt2(kClsH128)) > 0) CVB_TRY((launch_warp<W, 256>(e, p, lst(kClsH128), n)));
   if ((n = cnt2(kClsH512)) > 0) CVB_TRY((launch_warp<W, 1024>(e, p, lst(kClsH512), n)));
   if ((n = cnt2(kClsH2K)) > 0) CVB_TRY((launch_block<W, 4096, 256>(e, p, lst(kClsH2K), n)));
   if ((n = cnt2(kClsH8K)) > 0) CVB_TRY((launch_block<W, 16384, 1024>(e, p, lst(kClsH8K), n)));
-  if ((n = e->class_start[kClsGiant + 1] - e->class_start[kClsC2]) > 0) {  // cluster classes + giants
+  if ((n = cs[kClsGiant + 1] - cs[kClsC2]) > 0) {  // cluster classes + giants
     const int grid = static_cast<int>(n < e->giant_blocks ? n : e->giant_blocks);
     k_sweep_block<W, 1024, 1024, true><<<grid, 1024, 0, e->stream>>>(p, lst(kClsC2), (int)n, e->giant.p,
                                                                     e->giant_stride, e->giant_log2cap);
@@ -477,7 +491,7 @@ int launch_lm_block(cvb_engine *e, cudaStream_t st, const LmParams &p, int64_t f
 int launch_sweep_u32(cvb_engine *e) {
   cudaStream_t st = e->stream;
   const bool lm = e->use_lm && e->lm_ready;
-  const bool first_sweep = e->sweeps_in_phase == 0 && e->rows_simple && e->use_first_sweep;
+  const bool first_sweep = e->sweeps_in_phase == 0 && e->rows_simple && e->use_first_sweep && !e->ovr;
   const bool remap = lm && e->remap && !e->use_split;  // the split-gather A/B variant indexes labels[] by vertex id
   k_pack_labels<<<grid_for(e->nvg, 256), 256, 0, st>>>(e->nvg, e->sweep_labels(), e->cdeg.p, e->csize.p,
                                                        e->packed.p, remap ? e->rank.p : nullptr);
@@ -501,21 +515,30 @@ int launch_sweep_u32(cvb_engine *e) {
   p.cdeg32 = nullptr;
   // singleton bypass: needs community sizes that agree with the labels; early termination rotates the labels of
   // frozen vertices WITHOUT updating the community info (louvain.cpp:174-186, mirrored), so it is off there
-  p.simple_rows = (e->rows_simple && !e->et_no_deltas && !getenv("CVB_NO_SINGLETON_SKIP")) ? 1 : 0;
+  // (and in colour steps: the community info is updated colour by colour while the labels stay those of the iteration)
+  p.simple_rows = (e->rows_simple && !e->et_no_deltas && !e->ovr && !getenv("CVB_NO_SINGLETON_SKIP")) ? 1 : 0;
   if (e->use_split) {
     CVB_TRY(e->cdeg32.ensure(e->nvg + 1));
     k_cdeg32<<<grid_for(e->nvg, 256), 256, 0, st>>>(e->nvg, e->cdeg.p, e->cdeg32.p);
     e->launches++;
     p.cdeg32 = e->cdeg32.p;
   }
-  auto cnt = [&](int c) { return e->class_start[c + 1] - e->class_start[c]; };
-  auto lst = [&](int c) { return e->list.p + e->class_start[c]; };
+  // class ranges: the degree-class list of the graph, or — in a colour step — the range of (colour, class)
+  // in the per-colour lists for the classes below kClsC2 (the big classes always run over all their vertices)
+  auto cpos = [&](int c) -> int64_t {
+    return (e->ovr && c < kClsC2) ? e->col_start[e->ovr_color * kNumClasses + c] : e->class_start[c];
+  };
+  auto cnt = [&](int c) -> int64_t {
+    return (e->ovr && c < kClsC2) ? e->col_start[e->ovr_color * kNumClasses + c + 1] - e->col_start[e->ovr_color * kNumClasses + c]
+                                  : e->class_start[c + 1] - e->class_start[c];
+  };
+  auto lst = [&](int c) { return ((e->ovr && c < kClsC2) ? e->col_list.p : e->list.p) + cpos(c); };
   int64_t n;
   LmParams q{};
   if (lm) {
-    q.vrec = e->vrec.p;
+    q.vrec = e->ovr ? e->col_vrec.p : e->vrec.p;
     q.tails = remap ? e->tails_r.p : e->tails.p;
-    q.remap = remap ? (e->nvl == e->nvg ? 1 : 2) : 0;
+    q.remap = remap ? ((e->nvl == e->nvg && !e->ovr) ? 1 : 2) : 0;  // colour lists: rank[] lookup
     q.rank = e->rank.p;
     q.rank_top = static_cast<int>(e->nvl - 1);
     q.simple_rows = p.simple_rows;
@@ -529,7 +552,7 @@ int launch_sweep_u32(cvb_engine *e) {
     q.ddeg = p.ddeg;
     q.dsize = p.dsize;
   }
-  auto pos = [&](int c) { return e->class_start[c]; };
+  auto pos = [&](int c) { return cpos(c); };
   if (first_sweep) {
     // singleton start: nothing to merge, table-free kernels (one launch per width)
     auto span = [&](int c0, int c1) { return e->class_start[c1 + 1] - e->class_start[c0]; };
@@ -617,7 +640,9 @@ int launch_sweep_u32(cvb_engine *e) {
   // measured slower on B200 — DESIGN.md section 5).
   const int gcls = e->global_table_class();
   const bool big = lm && e->big_ready;
-  if (big && (n = e->class_start[kClsGiant + 1] - e->class_start[kClsC2]) > 0) {
+  CVB_CHECK(!e->ovr || big || e->class_start[kClsGiant + 1] == e->class_start[kClsC2], CVB_ERR_STATE,
+            "colouring needs the default big-vertex path (CVB_BIG / CVB_LM left at their defaults)");
+  if (big && !(e->ovr && !e->ovr_big) && (n = e->class_start[kClsGiant + 1] - e->class_start[kClsC2]) > 0) {
     BigParams bp{};
     bp.chunk_owner = e->big_owner.p;
     bp.chunk_start = e->big_layout.p;
@@ -631,6 +656,13 @@ int launch_sweep_u32(cvb_engine *e) {
     bp.cand_key = e->bg_cand_key.p;
     bp.flags = e->d_flags.p;
     bp.big_first = static_cast<int>(pos(kClsC2));
+    LmParams qb = q;
+    if (e->ovr) {  // colour step: every big vertex is evaluated, k_color_fix_big keeps the ones of this colour
+      qb.vrec = e->vrec.p;
+      qb.remap = remap ? 1 : 0;
+      qb.ddeg = nullptr;
+      qb.dsize = nullptr;
+    }
     constexpr size_t kStageSmem = size_t(8) << 13, kPassSmem = size_t(8) << 13;
     auto stage = e->unit_weights ? k_big_stage<true> : k_big_stage<false>;
     const int occ1 = lm_setup(e, reinterpret_cast<const void *>(stage), 512, kStageSmem);
@@ -638,10 +670,17 @@ int launch_sweep_u32(cvb_engine *e) {
     CVB_CHECK(occ1 > 0 && occ2 > 0, CVB_ERR_CUDA, "big-vertex kernels: cannot configure (%s)",
               cudaGetErrorString(cudaGetLastError()));
     const int64_t cap1 = static_cast<int64_t>(e->num_sms) * occ1, cap2 = static_cast<int64_t>(e->num_sms) * occ2;
-    stage<<<static_cast<int>(e->big_chunks < cap1 ? e->big_chunks : cap1), 512, kStageSmem, e->S(1)>>>(q, bp, e->big_chunks);
-    k_big_pass<<<static_cast<int>(e->bg_items < cap2 ? e->bg_items : cap2), 512, kPassSmem, e->S(1)>>>(q, bp, e->bg_items);
-    k_big_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->S(1)>>>(q, bp, static_cast<int>(n));
+    stage<<<static_cast<int>(e->big_chunks < cap1 ? e->big_chunks : cap1), 512, kStageSmem, e->S(1)>>>(qb, bp, e->big_chunks);
+    k_big_pass<<<static_cast<int>(e->bg_items < cap2 ? e->bg_items : cap2), 512, kPassSmem, e->S(1)>>>(qb, bp, e->bg_items);
+    k_big_final<<<static_cast<int>((n * 32 + 127) / 128), 128, 0, e->S(1)>>>(qb, bp, static_cast<int>(n));
     e->launches += 3;
+    if (e->ovr) {
+      k_color_fix_big<<<static_cast<int>((n + 127) / 128), 128, 0, e->S(1)>>>(
+          e->list.p + e->class_start[kClsC2], static_cast<int>(n), e->col_color.p, e->col_num, e->ovr_color,
+          e->lab[e->targ].p, e->lab[e->curr].p, e->cw.p, e->col_bak_t.p, e->col_bak_cw.p, e->vdeg.p, e->ddeg.p,
+          e->dsize.p);
+      e->launches++;
+    }
   }
   const bool mp = lm && e->mp_ready && !big;
   if (mp && (n = e->class_start[kClsGiant] - e->class_start[kClsC2]) > 0) {
@@ -1202,6 +1241,8 @@ void cvb_destroy(cvb_engine *e) {
   e->partials.release(); e->d_sums.release(); e->ticket.release(); e->d_flags.release();
   e->h_sums.release(); e->staging.release(); e->staging2.release(); e->giant.release(); e->h_stage.release();
   e->packed.release(); e->giant_layout.release(); e->gslots.release(); e->pair_keys.release(); e->pair_w.release();
+  e->col_color.release(); e->col_keys.release(); e->col_keys2.release(); e->col_list.release(); e->col_ids.release();
+  e->col_vrec.release(); e->col_bak_t.release(); e->col_bak_cw.release();
   e->cdeg32.release(); e->vrec.release(); e->selfw.release(); e->rank.release(); e->tails_r.release();
   e->bg_log2p.release(); e->bg_item_start.release(); e->bg_item_owner.release(); e->bg_records.release();
   e->bg_cursor.release(); e->bg_own.release(); e->bg_cand_key.release(); e->bg_cand_gain.release();
@@ -1549,6 +1590,13 @@ int cvb_get_labels(cvb_engine *e, int which, int64_t *out) {
 int cvb_get_cluster_weight(cvb_engine *e, double *out) {
   CVB_CHECK(e && e->phase_ready && out, CVB_ERR_STATE, "no phase");
   CVB_CUDA(cudaMemcpyAsync(out, e->cw.p, e->nvl * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CVB_CUDA(cudaStreamSynchronize(e->stream));
+  return CVB_OK;
+}
+
+int cvb_get_colors(cvb_engine *e, int32_t *out) {
+  CVB_CHECK(e && e->graph_ready && out && e->col_color.p, CVB_ERR_STATE, "cvb_get_colors: no colouring was run");
+  CVB_CUDA(cudaMemcpyAsync(out, e->col_color.p, e->nvl * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   CVB_CUDA(cudaStreamSynchronize(e->stream));
   return CVB_OK;
 }
@@ -2058,13 +2106,162 @@ int cvb_phase_run_et(cvb_engine *e, double lower, double thresh, int et_type, do
   return CVB_OK;
 }
 
+// distColoringMultiHashMinMax (coloring.cpp:3-72) on one GPU: rounds of k_color_round with nHash =
+// max_colors / 2 hash functions until 70 % (MAX_COVG, main.cpp:26) of the vertices are coloured or a round
+// colours nothing; the colour ids of round r start at r * 2 * nHash and the seed is re-hashed per round.
+// Returns the reference's numColors (= rounds * 2 * nHash) and leaves the colours in e->col_color.
+static int color_graph(cvb_engine *e, int max_colors, int *num_colors_out) {
+  const int n_hash = max_colors / 2;  // main.cpp:245
+  CVB_CHECK(n_hash >= 0 && n_hash <= 16, CVB_ERR_ARG, "max_colors must be in 0..32 (option -c)");
+  cudaStream_t st = e->stream;
+  const int64_t nvl = e->nvl;
+  CVB_TRY(e->col_color.ensure(nvl + 1));
+  CVB_TRY(e->et_count.ensure(4));
+  CVB_CUDA(cudaMemsetAsync(e->col_color.p, 0xff, (nvl + 1) * sizeof(int32_t), st));  // -1 = uncoloured
+  CVB_CUDA(cudaMemsetAsync(e->et_count.p, 0, 4 * sizeof(unsigned int), st));
+  unsigned int seed = 1012u, coloured = 0, last = 0;
+  int next_color = 0;
+  const int64_t target = (e->nvg * 70) / 100;
+  while (true) {
+    if (nvl > 0 && n_hash > 0) {
+      k_color_round<<<static_cast<int>((nvl * 32 + 255) / 256), 256, 0, st>>>(
+          e->offsets.p, e->tails.p, nvl, static_cast<vid_t>(e->base), n_hash, next_color, seed, e->col_color.p,
+          e->et_count.p);
+      e->launches++;
+    }
+    CVB_CUDA(cudaMemcpyAsync(&coloured, e->et_count.p, sizeof coloured, cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(cudaStreamSynchronize(st));
+    const bool finished = static_cast<int64_t>(coloured) >= target || coloured == last;  // coloring.cpp:50
+    next_color += 2 * n_hash;
+    seed = color_hash(seed, 0u);
+    last = coloured;
+    if (finished) break;
+  }
+  *num_colors_out = next_color;
+  return CVB_OK;
+}
+
+// per-colour degree-class lists: vertices sorted by (colour bucket, degree class), uncoloured in the last
+// bucket (louvain.cpp:806-842), with the per-vertex records of lm.cuh in the same order
+static int color_lists(cvb_engine *e, int num_color) {
+  cudaStream_t st = e->stream;
+  const int64_t nvl = e->nvl;
+  const int nkeys = num_color * kNumClasses;
+  e->col_num = num_color;
+  CVB_TRY(e->col_keys.ensure(nvl + 1));
+  CVB_TRY(e->col_keys2.ensure(nvl + 1));
+  CVB_TRY(e->col_ids.ensure(nvl + 1));
+  CVB_TRY(e->col_list.ensure(nvl + 1));
+  e->col_start.assign(static_cast<size_t>(nkeys) + 1, 0);
+  if (nvl == 0) return CVB_OK;
+  k_color_keys<<<grid_for(nvl, 256), 256, 0, st>>>(e->offsets.p, e->col_color.p, nvl, num_color, e->col_keys.p,
+                                                   e->col_ids.p);
+  int bits = 1;
+  while ((1 << bits) < nkeys) bits++;
+  size_t tb = 0;
+  CVB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, e->col_keys.p, e->col_keys2.p, e->col_ids.p, e->col_list.p,
+                                           static_cast<int>(nvl), 0, bits, st));
+  CVB_TRY(e->staging2.ensure(tb + static_cast<size_t>(nkeys) * sizeof(unsigned int) + 64));
+  CVB_CUDA(cub::DeviceRadixSort::SortPairs(e->staging2.p, tb, e->col_keys.p, e->col_keys2.p, e->col_ids.p,
+                                           e->col_list.p, static_cast<int>(nvl), 0, bits, st));
+  unsigned int *hist = reinterpret_cast<unsigned int *>(e->staging2.p + ((tb + 15) / 16) * 16);
+  CVB_CUDA(cudaMemsetAsync(hist, 0, static_cast<size_t>(nkeys) * sizeof(unsigned int), st));
+  k_key_histogram<<<grid_for(nvl, 256), 256, 0, st>>>(e->col_keys.p, nvl, hist);
+  e->launches += 3;
+  std::vector<unsigned int> h(nkeys);
+  CVB_CUDA(cudaMemcpyAsync(h.data(), hist, static_cast<size_t>(nkeys) * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CVB_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k < nkeys; ++k) e->col_start[k + 1] = e->col_start[k] + h[k];
+  if (e->lm_ready) {
+    CVB_TRY(e->col_vrec.ensure(nvl + 1));
+    k_build_vrec<<<grid_for(nvl, 256), 256, 0, st>>>(e->col_list.p, e->offsets.p, e->vdeg.p, nvl, e->col_vrec.p);
+    e->launches++;
+  }
+  return CVB_OK;
+}
+
+// distLouvainMethodWithColoring (louvain.cpp:756-949) on one GPU.  Inside an iteration the colour
+// buckets are swept one after the other: every step reads the labels of the iteration's start and the
+// community info as the earlier colours of the same iteration left it (louvain.cpp:864-899); the new labels
+// take effect together at the end of the iteration.  The sweep kernels are the ordinary ones, launched over
+// the (colour, class) ranges of the per-colour lists.
+int cvb_phase_run_color(cvb_engine *e, double lower, double thresh, int max_colors, double *q_out, int *iters_out,
+                        int *num_colors_out) {
+  CVB_CHECK(e && e->graph_ready, CVB_ERR_STATE, "cvb_phase_run_color: no graph uploaded");
+  CVB_CHECK(e->nvl == e->nvg, CVB_ERR_STATE, "cvb_phase_run_color is the one-GPU driver");
+  int num_colors = 0;
+  CVB_TRY(color_graph(e, max_colors, &num_colors));
+  if (num_colors_out) *num_colors_out = num_colors;
+  const int num_color = num_colors + 1;  // main.cpp:259: the last bucket holds the uncoloured vertices
+  if (num_color == 1) return cvb_phase_run(e, lower, thresh, 0, q_out, iters_out);  // louvain.cpp:764-768
+  CVB_TRY(color_lists(e, num_color));
+  cudaStream_t st = e->stream;
+  const int64_t nvl = e->nvl;
+  const int64_t nbig = e->mode == CVB_WEIGHTS_U32 ? e->class_start[kClsGiant + 1] - e->class_start[kClsC2] : 0;
+  const vid_t *big_list = e->list.p + e->class_start[kClsC2];
+  if (nbig > 0) {
+    CVB_TRY(e->col_bak_t.ensure(nbig));
+    CVB_TRY(e->col_bak_cw.ensure(nbig));
+  }
+  CVB_TRY(cvb_phase_begin(e, 0.0));
+  struct Restore { cvb_engine *e; ~Restore() { e->ovr = false; } } restore{e};
+  double prev = lower, cur = -1.0;
+  int iters = 0;
+  while (true) {
+    iters++;
+    CVB_CUDA(cudaMemsetAsync(e->cw.p, 0, nvl * sizeof(double), st));  // louvain.cpp:857-858
+    if (nbig > 0) {
+      k_color_bak_init<<<static_cast<int>((nbig + 127) / 128), 128, 0, st>>>(big_list, static_cast<int>(nbig),
+                                                                            e->lab[e->targ].p, e->col_bak_t.p,
+                                                                            e->col_bak_cw.p);
+      e->launches++;
+    }
+    for (int ci = 0; ci < num_color; ++ci) {
+      const int64_t *cs = e->col_start.data() + static_cast<size_t>(ci) * kNumClasses;
+      if (cs[kNumClasses] == cs[0]) continue;  // no vertex of this colour
+      e->ovr = true;
+      e->ovr_color = ci;
+      e->ovr_big = cs[kNumClasses] > cs[kClsC2];
+      const int rc = cvb_sweep(e);
+      e->ovr = false;
+      CVB_TRY(rc);
+      CVB_TRY(apply_reduce_async(e));  // louvain.cpp:887-893; the sums of the last colour are the iteration's
+    }
+    CVB_CUDA(cudaStreamSynchronize(st));
+    double sums[3];
+    memcpy(sums, e->h_sums.p, sizeof sums);
+    CVB_CHECK(sums[2] == 0.0, CVB_ERR_CAPACITY, "a partition bucket of the big-vertex path overflowed; rerun with CVB_BIG=0");
+    cur = cvb_modularity_from_sums(e, sums);
+    if ((cur - prev) < thresh) break;
+    prev = cur;
+    if (prev < lower) prev = lower;
+    CVB_TRY(cvb_rotate_labels(e));
+  }
+  if (q_out) *q_out = prev;
+  if (iters_out) *iters_out = iters;
+  return CVB_OK;
+}
+
+static int louvain_run_impl(cvb_engine *e, int max_levels, int flags, int et_type, double et_delta, int max_colors,
+                            double *level_q, int *level_iters, int64_t *level_nv, int64_t *comm_out);
+
 int cvb_louvain_run_ex(cvb_engine *e, int max_levels, int flags, double *level_q, int *level_iters,
                        int64_t *level_nv, int64_t *comm_out) {
-  return cvb_louvain_run_et(e, max_levels, flags, 0, 1.0, level_q, level_iters, level_nv, comm_out);
+  return louvain_run_impl(e, max_levels, flags, 0, 1.0, -1, level_q, level_iters, level_nv, comm_out);
 }
 
 int cvb_louvain_run_et(cvb_engine *e, int max_levels, int flags, int et_type, double et_delta, double *level_q,
                        int *level_iters, int64_t *level_nv, int64_t *comm_out) {
+  return louvain_run_impl(e, max_levels, flags, et_type, et_delta, -1, level_q, level_iters, level_nv, comm_out);
+}
+
+int cvb_louvain_run_color(cvb_engine *e, int max_levels, int flags, int max_colors, double *level_q,
+                          int *level_iters, int64_t *level_nv, int64_t *comm_out) {
+  return louvain_run_impl(e, max_levels, flags, 0, 1.0, max_colors, level_q, level_iters, level_nv, comm_out);
+}
+
+static int louvain_run_impl(cvb_engine *e, int max_levels, int flags, int et_type, double et_delta, int max_colors,
+                            double *level_q, int *level_iters, int64_t *level_nv, int64_t *comm_out) {
   if (!e || !e->graph_ready) { set_error("cvb_louvain_run: no graph uploaded"); return CVB_ERR_STATE; }
   if (e->nvl != e->nvg) { set_error("cvb_louvain_run is the one-GPU driver"); return CVB_ERR_STATE; }
   cudaStream_t st = e->stream;
@@ -2086,8 +2283,10 @@ int cvb_louvain_run_et(cvb_engine *e, int max_levels, int flags, int et_type, do
       const int sp = phase % 13;
       threshold = sp <= 2 ? 1.0e-3 : sp <= 6 ? 1.0e-4 : sp <= 9 ? 1.0e-5 : 1.0e-6;
     }
-    int rc = et_type ? cvb_phase_run_et(e, curr, threshold, et_type, et_delta, &curr, &iters)  // main.cpp:326-341
-                     : cvb_phase_run(e, curr, threshold, 0, &curr, &iters);                    // main.cpp:344
+    int rc = (max_colors >= 0 && phase == 0)  // option -c: the first phase only, main.cpp:242-282
+                 ? cvb_phase_run_color(e, curr, threshold, max_colors, &curr, &iters, nullptr)
+                 : et_type ? cvb_phase_run_et(e, curr, threshold, et_type, et_delta, &curr, &iters)  // main.cpp:326-341
+                           : cvb_phase_run(e, curr, threshold, 0, &curr, &iters);                    // main.cpp:344
     if (rc != CVB_OK) return rc;
     tot_iters += iters;
     if ((curr - prev) > threshold) {  // main.cpp:361
@@ -2278,8 +2477,6 @@ int cvb_dist_phase_begin(cvb_engine *e) {
       e->remap = true;
     }
   }
-  d.stage_n = 0;
-  for (auto &x : d.stage_ms) x = 0.0;
   return CVB_OK;
 }
 

@@ -524,6 +524,120 @@ __global__ void k_et_rotate(int64_t nvl, int num_iters, int prob, double one_min
   }
 }
 
+// ---- distance-1 colouring (option -c; coloring.cpp:3-200) -------------------------------------
+// The reference's integer hash (coloring.cpp:74-85).
+__host__ __device__ inline unsigned int color_hash(unsigned int a, unsigned int seed) {
+  a ^= seed;
+  a = (a + 0x7ed55d16u) + (a << 12);
+  a = (a ^ 0xc761c23cu) + (a >> 19);
+  a = (a + 0x165667b1u) + (a << 5);
+  a = (a ^ 0xd3a2646cu) + (a << 9);
+  a = (a + 0xfd7046c5u) + (a << 3);
+  a = (a ^ 0xb55a4f09u) + (a >> 16);
+  return a;
+}
+
+// One round of distColoringIteration (coloring.cpp:87-200), one warp per vertex.  An uncoloured vertex
+// compares its nHash hash values with those of its neighbours that were not coloured in an EARLIER
+// round (colours assigned in this round are >= next_color and count as uncoloured, so the round does
+// not depend on the order in which vertices are visited); where it is the strict minimum / maximum of
+// hash t it may take colour 2t / 2t+1 (+ next_color), and it picks the (id mod #possible)-th of them.
+__global__ void k_color_round(const eid_t *__restrict__ offsets, const vid_t *__restrict__ tails, int64_t nv, vid_t base,
+                              int n_hash, int next_color, unsigned int seed, int32_t *__restrict__ color,
+                              unsigned int *__restrict__ colored_count) {
+  const int64_t v = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  if (v >= nv) return;
+  if (color[v] != -1) return;  // warp-uniform
+  const unsigned int self = static_cast<unsigned int>(v + base);
+  unsigned int not_min = 0u, not_max = 0u;
+  for (eid_t e = offsets[v] + lane; e < offsets[v + 1]; e += 32) {
+    const vid_t t = tails[e];
+    if (static_cast<unsigned int>(t) == self) continue;  // self-loops are ignored
+    const int32_t ct = color[t - base];
+    if (ct != -1 && ct < next_color) continue;  // coloured in an earlier round
+    for (int h = 0; h < n_hash; ++h) {
+      const unsigned int vh = color_hash(self, seed + 1043u * h);
+      const unsigned int jh = color_hash(static_cast<unsigned int>(t), seed + 1043u * h);
+      if (vh <= jh) not_max |= 1u << h;
+      if (vh >= jh) not_min |= 1u << h;
+    }
+  }
+  not_min = __reduce_or_sync(0xffffffffu, not_min);
+  not_max = __reduce_or_sync(0xffffffffu, not_max);
+  if (lane != 0) return;
+  const int possible = 2 * n_hash - __popc(not_min) - __popc(not_max);
+  if (possible <= 0) return;
+  const int col_id = static_cast<int>(static_cast<int64_t>(self) % possible);
+  int this_id = 0;
+  for (int h = 0; h < n_hash; ++h) {
+    if (!(not_min & (1u << h)) && col_id == this_id) {
+      color[v] = 2 * h + next_color;
+      atomicAdd(colored_count, 1u);
+      return;
+    }
+    this_id += !(not_min & (1u << h));
+    if (!(not_max & (1u << h)) && col_id == this_id) {
+      color[v] = 2 * h + 1 + next_color;
+      atomicAdd(colored_count, 1u);
+      return;
+    }
+    this_id += !(not_max & (1u << h));
+  }
+}
+
+// sort key of a vertex for the per-colour class lists: (colour bucket, degree class); uncoloured vertices go
+// to the last bucket (louvain.cpp:813, 829)
+__global__ void k_color_keys(const eid_t *__restrict__ offsets, const int32_t *__restrict__ color, int64_t nv,
+                             int num_color, int32_t *__restrict__ keys, vid_t *__restrict__ ids) {
+  for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < nv;
+       v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = color[v] < 0 ? num_color - 1 : color[v];
+    keys[v] = b * kNumClasses + degree_class(offsets[v + 1] - offsets[v]);
+    ids[v] = static_cast<vid_t>(v);
+  }
+}
+__global__ void k_key_histogram(const int32_t *__restrict__ keys, int64_t n, unsigned int *__restrict__ hist) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    atomicAdd(&hist[keys[i]], 1u);
+}
+
+// Big vertices (above 8192 entries) in a colour step: their kernels ran over ALL of them with the delta
+// atomics off; vertices of the current colour keep the result and contribute their move, the others get
+// the values of their own colour step (or of the start of the iteration) back.
+__global__ void k_color_fix_big(const vid_t *__restrict__ big_list, int nbig, const int32_t *__restrict__ color,
+                                int num_color, int ci, vid_t *__restrict__ target, const vid_t *__restrict__ curr,
+                                double *__restrict__ cw, vid_t *__restrict__ bak_t, double *__restrict__ bak_cw,
+                                const double *__restrict__ vdeg, double *__restrict__ ddeg, int32_t *__restrict__ dsize) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nbig) return;
+  const vid_t v = big_list[i];
+  const int b = color[v] < 0 ? num_color - 1 : color[v];
+  if (b == ci) {
+    bak_t[i] = target[v];
+    bak_cw[i] = cw[v];
+    const vid_t t = target[v], c = curr[v];
+    if (t != c) {
+      const double d = vdeg[v];
+      atomicAdd(&ddeg[t], d);
+      atomicAdd(&dsize[t], 1);
+      atomicAdd(&ddeg[c], -d);
+      atomicAdd(&dsize[c], -1);
+    }
+  } else {
+    target[v] = bak_t[i];
+    cw[v] = bak_cw[i];
+  }
+}
+__global__ void k_color_bak_init(const vid_t *__restrict__ big_list, int nbig, const vid_t *__restrict__ target,
+                                 vid_t *__restrict__ bak_t, double *__restrict__ bak_cw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nbig) return;
+  bak_t[i] = target[big_list[i]];
+  bak_cw[i] = 0.0;
+}
+
 // ---- boundary-call helpers ---------------------------------------------------
 __global__ void k_scatter_labels(int64_t n, const int64_t *__restrict__ idx, const int64_t *__restrict__ val,
                                  vid_t *__restrict__ dst) {

@@ -277,16 +277,21 @@ class DistLouvain:
         extra 1e-6 pass main.cpp:436-441 runs right before exiting changes no reported level and no
         output file, so it is not run.)"""
         level_q, level_iters, level_nv = [], [], []
+        self.seconds = {"phases": 0.0, "coarsening": 0.0}  # host clock; both stages end with a host sync
         comm, comm_ref, nv0 = None, None, self.nvg
         curr, prev, tot_iters, phase = -1.0, -1.0, 0, 0
         while True:
             nv = self.nvg
             if threshold_cycling:
                 threshold = self.cycled_threshold(phase)  # short_phase == phase until the 200-phase cap
+            t0 = time.perf_counter()
             curr, iters = self.run_phase(lower=curr, thresh=threshold)
+            t1 = time.perf_counter()
+            self.seconds["phases"] += t1 - t0
             tot_iters += iters
             if (curr - prev) > threshold:  # main.cpp:361
                 newid, _ = self.coarsen()  # main.cpp:413
+                self.seconds["coarsening"] += time.perf_counter() - t1
                 if reference_numbering:
                     cv = self.last_cvect.long()
                     ranks = torch.searchsorted(torch.unique(cv), cv)  # unique() returns the values sorted

@@ -298,6 +298,20 @@ int cvb_phase_run_et(cvb_engine *e, double lower, double thresh, int et_type, do
 int cvb_louvain_run_et(cvb_engine *e, int max_levels, int flags, int et_type, double et_delta,
                        double *level_q, int *level_iters, int64_t *level_nv, int64_t *comm_out);
 
+/* Distance-1 colouring, option -c max_colors (main.cpp:242-282, 600-601): distColoringMultiHashMinMax
+ * (coloring.cpp:3-200, nHash = max_colors / 2, 70 % coverage target) followed by
+ * distLouvainMethodWithColoring (louvain.cpp:756-949) — inside an iteration the colour buckets are swept
+ * one after the other against the community info the earlier buckets left.  *num_colors_out = the
+ * reference's "Number of colors (2*nHash)".  max_colors < 2 runs the plain phase, as the reference does.
+ * One GPU; not combined with early termination. */
+int cvb_phase_run_color(cvb_engine *e, double lower, double thresh, int max_colors, double *q_out,
+                        int *iters_out, int *num_colors_out);
+/* cvb_louvain_run_ex with the FIRST phase run by cvb_phase_run_color (the reference colours phase 0 only). */
+int cvb_louvain_run_color(cvb_engine *e, int max_levels, int flags, int max_colors, double *level_q,
+                          int *level_iters, int64_t *level_nv, int64_t *comm_out);
+/* The colours of the last cvb_phase_run_color (-1 = uncoloured), nv_local values. */
+int cvb_get_colors(cvb_engine *e, int32_t *out);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Kernels launched by this engine since creation (bench.py "gpu_launches"). */
 int64_t cvb_launch_count(const cvb_engine *e);

@@ -1,0 +1,121 @@
+"""Option -c (distance-1 colouring + coloured phase 0): the emulation against the reference CLI (CPU),
+the GPU path against both."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import color_emulation as ce
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "oracle", "_ref", "gc_cpu64")
+
+
+def _graph(name):
+    from cuvite_b200 import graphgen as gg
+    return gg.erdos_renyi(3000, 8.0, seed=1) if name == "er3000" else gg.rmat(13, seed=2)
+
+
+def _cli(tmp_path, g, max_colors):
+    from cuvite_b200 import vite_io
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/gc_cpu64 not built (needs /root/reference at build time)")
+    f = str(tmp_path / "g.bin")
+    vite_io.write_vite(f, g)
+    r = subprocess.run([EXE, "-f", f, "-c", str(max_colors)], capture_output=True, text=True, timeout=600,
+                       cwd=str(tmp_path), env=dict(os.environ, OMP_NUM_THREADS="4"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ncol = int(re.search(r"Number of colors \(2\*nHash\): (\d+)", r.stdout).group(1))
+    levels = re.findall(r"Level \d+, Modularity: ([0-9.eE+-]+), Clustering time: [^,]*, Iterations: (\d+)", r.stdout)
+    assert levels
+    return ncol, [(float(q), int(i)) for q, i in levels]
+
+
+@pytest.mark.parametrize("graph", ["er3000", "rmat13"])
+@pytest.mark.parametrize("max_colors", [8, 4])
+def test_emulation_matches_reference_cli(tmp_path, graph, max_colors):
+    """Pins the emulation: number of colours, level-0 modularity (6 digits, as printed) and iterations of
+    the reference's own `-c` run."""
+    from oracle.binding import Oracle
+    g = _graph(graph)
+    o, t, w = g.offsets.numpy(), g.tails.numpy(), g.weights.numpy().astype(np.float64)
+    ncol, levels = _cli(tmp_path, g, max_colors)
+    color, n = ce.colour(o, t, max_colors // 2)
+    assert n == ncol
+    q, it = ce.phase_color(Oracle(), o, t, w, color, n + 1)
+    assert f"{q:.6g}" == f"{levels[0][0]:.6g}" and it == levels[0][1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", ["er3000", "rmat13"])
+@pytest.mark.parametrize("max_colors", [8, 4, 2, 1])
+def test_gpu_colouring_and_coloured_phase_match_emulation(graph, max_colors):
+    """Colours bit for bit, number of colours, and the coloured phase (modularity EXACTLY — unit weights make
+    every sum an integer — and iterations) against the CPU emulation."""
+    from cuvite_b200.engine import GpuGraph
+    from oracle.binding import Oracle
+    g = _graph(graph)
+    o, t, w = g.offsets.numpy(), g.tails.numpy(), g.weights.numpy().astype(np.float64)
+    color, n = ce.colour(o, t, max_colors // 2)
+    orc = Oracle()
+    if n == 0:  # no hash function: the reference falls back to the plain phase (louvain.cpp:764-768)
+        want = orc.phase(o, t, w)
+        wq, wit = want.q, want.iters
+    else:
+        wq, wit = ce.phase_color(orc, o, t, w, color, n + 1)
+    gpu = GpuGraph()
+    try:
+        gpu.upload(o, t, w)
+        q, it, ncol = gpu.phase_run_color(max_colors)
+        assert ncol == n
+        assert np.array_equal(gpu.colors(), color)
+        assert (q, it) == (wq, wit)
+    finally:
+        gpu.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", ["er3000", "rmat13"])
+@pytest.mark.parametrize("max_colors", [8, 4])
+def test_gpu_full_run_with_colouring_matches_reference_cli(tmp_path, graph, max_colors):
+    """cvb_louvain_run_color == the reference CLI with -c: every level's modularity (as printed) and
+    cumulative iterations; only phase 0 is coloured (main.cpp:242)."""
+    from cuvite_b200.engine import GpuGraph
+    g = _graph(graph)
+    _, levels = _cli(tmp_path, g, max_colors)
+    gpu = GpuGraph()
+    try:
+        gpu.upload(g.offsets.numpy(), g.tails.numpy(), g.weights.numpy())
+        lq, li, _, _ = gpu.run(max_colors=max_colors)
+    finally:
+        gpu.close()
+    assert [f"{q:.6g}" for q in lq] == [f"{q:.6g}" for q, _ in levels]
+    assert li == [i for _, i in levels]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("real_weights", [False, True])
+def test_gpu_coloured_phase_on_hub_graph(real_weights):
+    """Hubs in every degree class, including the partition-then-hash path above 8192 entries (evaluated for all
+    big vertices in every colour step, kept for the step's own colour) and, with real weights, the F64 kernels
+    over the per-colour lists."""
+    from graphs import hub_graph, with_real_weights
+    from cuvite_b200.engine import GpuGraph
+    from oracle.binding import Oracle
+    o, t, w = hub_graph()
+    if real_weights:
+        o, t, w = with_real_weights(o, t, w)
+    w = np.asarray(w, np.float64)
+    color, n = ce.colour(np.asarray(o), np.asarray(t), 4)
+    wq, wit = ce.phase_color(Oracle(), np.asarray(o), np.asarray(t), w, color, n + 1)
+    gpu = GpuGraph()
+    try:
+        gpu.upload(o, t, w)
+        q, it, ncol = gpu.phase_run_color(8)
+        assert ncol == n and np.array_equal(gpu.colors(), color)
+        assert it == wit
+        assert (q == wq) if not real_weights else abs(q - wq) <= 1e-6
+    finally:
+        gpu.close()

@@ -3,6 +3,7 @@
 # DRAM bytes (roofline.traffic), ncu --set full of the three dominant kernels, C3 golden summary.
 set -x
 mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r02_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu.log
 python bench.py --steps 12 --warmup 3 > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_ref.err
 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,l1tex__throughput.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct \
