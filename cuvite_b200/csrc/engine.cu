@@ -2348,6 +2348,12 @@ int cvb_dist_init(cvb_engine *e, const void *id, int nbytes, int rank, int world
   ncclUniqueId uid;
   memcpy(&uid, id, sizeof uid);
   CVB_CUDA(cudaSetDevice(e->device));
+  // This communicator carries one 4 B/vertex all-gather and one 16-byte all-reduce per sweep.  Measured on 8
+  // B200s (profiles/r02_bench_n8*.json): with NVLink-SHARP (NVLS) channels set up, the label all-gather of a
+  // sweep took 0.70 ms against 0.25 ms without them (0.09 ms in isolation either way) — so NVLS is off unless
+  // the host program asked for it.  NCCL reads the variable when the first communicator of the process
+  // initialises; a host that created one earlier (torch.distributed) sets it itself (cuvite_b200/dist.py does).
+  setenv("NCCL_NVLS_ENABLE", "0", /*overwrite=*/0);
   CVB_NCCL(n->CommInitRank(&d.comm, world, uid, rank));
   return CVB_OK;
 }

@@ -317,6 +317,8 @@ class DistLouvain:
 
 def init_process_group(backend: str | None = None):
     """Read torchrun's environment; returns (rank, local_rank, world)."""
+    # before the first NCCL communicator of the process exists: see cvb_dist_init (engine.cu) for the measurement
+    os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
