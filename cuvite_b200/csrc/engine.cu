@@ -1273,7 +1273,7 @@ static int upload_narrowed(cvb_engine *e, const void *edges_aos, const int64_t *
   static const int nt = [] {
     if (const char *s = getenv("CVB_UPLOAD_THREADS")) return atoi(s) > 0 ? atoi(s) : 1;
     const unsigned hw = std::thread::hardware_concurrency();
-    return static_cast<int>(hw >= 32 ? 16 : (hw >= 4 ? hw / 2 : 1));
+    return static_cast<int>(hw >= 32 ? 16 : (hw >= 4 ? hw / 2 : 1));  // CVB_UPLOAD_THREADS overrides
   }();
   // Measured on the B200 host (round 2): from PINNED memory the plain 16-byte-per-entry DMA (~50 GB/s)
   // beats narrowing on the host cores, so the narrow path is taken for pageable sources only (what the
@@ -1310,17 +1310,22 @@ static int upload_narrowed(cvb_engine *e, const void *edges_aos, const int64_t *
       if (lo >= hi) break;
       th.emplace_back([=, &stat]() {
         Stat s = stat[t];
+        // branch-free body: range / integrality violations only set bits, sums are exact integers
+        int64_t bad = 0, nonunit = 0;
+        uint64_t sum = 0;
         for (int64_t i = lo; i < hi; ++i) {
           const int64_t tl = aos ? aos[i].tail : tails[i];
           const double w = aos ? aos[i].weight : weights[i];
-          if (!(w >= 0.0) || w >= 4294967296.0 || w != static_cast<double>(static_cast<uint32_t>(w)) || tl < 0 ||
-              tl > 2147483000LL)
-            s.bad = 1;
-          s.nonunit |= (w != 1.0);
-          s.sum += w;
+          const int64_t wi = static_cast<int64_t>(w);  // NaN / out of range -> INT64_MIN: caught by the range test
+          bad |= (wi >> 32) | (static_cast<double>(wi) != w) | (tl < 0) | (tl > 2147483000LL);
+          nonunit |= wi ^ 1;
+          sum += static_cast<uint64_t>(wi) & 0xffffffffu;
           ht[i] = static_cast<int32_t>(tl);
-          hw[i] = static_cast<uint32_t>(w);
+          hw[i] = static_cast<uint32_t>(wi);
         }
+        s.bad |= bad != 0;
+        s.nonunit |= nonunit != 0;
+        s.sum += static_cast<double>(sum);
         stat[t] = s;
       });
     }

@@ -366,7 +366,17 @@ def bench_multi(args, metric, unit, base_scale, measured_peak_gbs, ClockSampler,
     gpu = GpuGraph(stream=side.cuda_stream)
     b0, b1, ne_local = load_partition(gpu, g, rank, world)
     nv, ne = g.nv, g.ne
-    del g
+    # this rank's rows as the reference holds them (Graph::edgeListIndexes + Edge{int64 tail; double weight}
+    # AoS, distgraph.hpp) in pinned host memory: the input of the end-to-end leg below
+    import numpy as np
+    e_lo, e_hi = int(g.offsets[b0]), int(g.offsets[b1])
+    o_pin = torch.from_numpy((g.offsets[b0:b1 + 1] - e_lo).cpu().numpy()).pin_memory().numpy()
+    edges = np.empty(e_hi - e_lo, dtype=[("tail", "<i8"), ("weight", "<f8")])
+    edges["tail"] = g.tails[e_lo:e_hi].cpu().numpy()
+    edges["weight"] = g.weights[e_lo:e_hi].cpu().numpy()
+    edges_pin = torch.from_numpy(edges.view(np.uint8)).pin_memory()
+    edges_p = edges_pin.numpy().view(edges.dtype)
+    del g, edges
     torch.cuda.empty_cache()
     dl = DistLouvain(gpu, rank, world, nv)
 
@@ -419,6 +429,44 @@ def bench_multi(args, metric, unit, base_scale, measured_peak_gbs, ClockSampler,
     dist.all_reduce(launches)
     ne_max = torch.tensor([ne_local], dtype=torch.int64, device="cuda")
     dist.all_reduce(ne_max, op=dist.ReduceOp.MAX)
+
+    # ---- end to end: the N-rank distLouvainMethod(.., GpuGraph&) of adapter_resident.cpp, per phase: every rank
+    # ---- uploads ITS rows from pinned host memory (AoS), the ranks agree on ranges and weight mode, the phase
+    # ---- runs through cvb_dist_phase_run, and each rank reads its cvect back.  Host clock, max over ranks.
+    e2e = {"value": None, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16,
+           "api": "device-resident distributed phase; see N=1 for the host-buffer plugin path"}
+    if dl.native:
+        def resident_phases(min_sweeps):
+            sweeps = phases = 0
+            q = None
+            while sweeps < min_sweeps:
+                gpu.upload_aos(o_pin, edges_p, base=b0, nv_global=nv)
+                gpu.dist_set_parts(dl.parts)
+                gpu.dist_agree()
+                q, iters = gpu.dist_phase_run(-1.0, 1e-6)
+                gpu.labels(0)
+                sweeps += iters
+                phases += 1
+            return sweeps, phases, q
+
+        resident_phases(1)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res_sweeps, res_phases, res_q = resident_phases(args.steps)
+        torch.cuda.synchronize()
+        dist.barrier()
+        secs = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+        h2d = torch.tensor([edges_p.nbytes + o_pin.nbytes], dtype=torch.int64, device="cuda")
+        dist.all_reduce(h2d)
+        e2e = {"value": (ne / 2) * res_sweeps / float(secs.item()), "unit": unit, "sweeps": res_sweeps,
+               "h2d_bytes_per_step": int(int(h2d.item()) * res_phases / res_sweeps),
+               "d2h_bytes_per_step": int(nv * 8 * res_phases / res_sweeps), "phase_q": res_q,
+               "phase_q_equals_device_resident_run": bool(res_q == st["phase_q"]),
+               "api": "N-rank distLouvainMethod(.., GpuGraph&) (adapter_resident.cpp): per phase every rank runs "
+                      "cvb_graph_upload_host on its rows (pinned AoS) + cvb_dist_set_parts/agree + "
+                      "cvb_dist_phase_run + cvb_get_labels; bytes are the sum over ranks"}
     if rank == 0:
         clocks = sampler.stop()
         ms_per_step = float(ms.item()) / args.steps
@@ -445,8 +493,7 @@ def bench_multi(args, metric, unit, base_scale, measured_peak_gbs, ClockSampler,
                 "parity": ({**parity_record(scale, True, st["phase_q"], st["phase_iters"], None),
                             "q_per_iteration_gpu": st["qs"]} if parity_record else None),
                 "cpu_baseline": None,
-                "e2e": {"value": None, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16,
-                        "api": "device-resident distributed phase; see N=1 for the host-buffer plugin path"},
+                "e2e": e2e,
                 "gpu_launches": int(launches.item()), "clocks": clocks}
         print(json.dumps(line), flush=True)
     bad = bool(parity_record and parity_record(scale, True, st["phase_q"], st["phase_iters"], None)["ok"] is False)
