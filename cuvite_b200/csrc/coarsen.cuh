@@ -124,16 +124,27 @@ __global__ void k_sum_segments_f64(const double *__restrict__ w_sorted, const in
   }
 }
 
-__global__ void k_sum_segments_u32(const uint32_t *__restrict__ w_sorted, const int64_t *__restrict__ seg_start,
-                                   int64_t nseg, int64_t ne, uint32_t *__restrict__ out) {
-  const int64_t s = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+// uint32 weights (exact in any order): one thread per SORTED ENTRY.  The entries of a merged pair are contiguous,
+// so a warp first adds the runs it holds with a segmented shuffle scan (seg ids ascend) and only the last lane
+// of every run issues an atomic — one per merged pair in the common case, one per warp and run for the long
+// runs of heavy community pairs.  `out` must be zero.  (Round 2 launch list, R-MAT scale 22: the former
+// warp-per-merged-pair kernel took 17.7 ms per level — 100 M warps for runs of length 1-2 — against 1.4 ms for
+// a radix-sort pass over the same entries.)
+__global__ void k_sum_segments_u32(const uint32_t *__restrict__ w_sorted, const int32_t *__restrict__ seg_incl,
+                                   int64_t ne, uint32_t *__restrict__ out) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // grid covers ne exactly once
   const unsigned lane = threadIdx.x & 31u;
-  if (s >= nseg) return;
-  const int64_t a = seg_start[s], b = (s + 1 < nseg) ? seg_start[s + 1] : ne;
-  uint32_t acc = 0u;
-  for (int64_t e = a + lane; e < b; e += 32) acc += w_sorted[e];
-  acc = __reduce_add_sync(0xffffffffu, acc);
-  if (lane == 0) out[s] = acc;
+  const bool valid = e < ne;
+  const int32_t sg = valid ? seg_incl[e] : -1;
+  uint32_t w = valid ? w_sorted[e] : 0u;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t wu = __shfl_up_sync(0xffffffffu, w, d);
+    const int32_t su = __shfl_up_sync(0xffffffffu, sg, d);
+    if (lane >= static_cast<unsigned>(d) && su == sg) w += wu;
+  }
+  const int32_t sn = __shfl_down_sync(0xffffffffu, sg, 1);
+  if (valid && (lane == 31u || sn != sg)) atomicAdd(&out[sg - 1], w);
 }
 
 }  // namespace cvb

@@ -3,6 +3,9 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <thread>
 #include <map>
 #include <mutex>
@@ -1268,19 +1271,77 @@ void cvb_destroy(cvb_engine *e) {
 // was bound by exactly that copy.  Worker threads narrow fixed-size chunks into pinned staging while the
 // copies of the finished chunks are already in flight.  Returns 1 when the device arrays are filled and
 // e->mode is set, 0 when the graph needs the general path (a non-integer / negative / huge weight).
-static int upload_narrowed(cvb_engine *e, const void *edges_aos, const int64_t *tails, const double *weights,
-                           int64_t ne) {
+// Host worker pool of the narrowing upload: created once per process (thread creation costs more than
+// narrowing a 4 M-entry chunk), workers sleep between uploads.  A job is `npieces` independent pieces handed
+// out through an atomic counter; the caller learns about finished pieces through `done`.
+namespace {
+struct NarrowPool {
+  std::mutex m;
+  std::condition_variable cv;
+  std::vector<std::thread> th;
+  uint64_t gen = 0;
+  std::function<void(int64_t)> fn;
+  int64_t npieces = 0;
+  std::atomic<int64_t> next{0};
+  std::atomic<int> active{0};
+
+  explicit NarrowPool(int nt) {
+    for (int t = 0; t < nt; ++t) {
+      th.emplace_back([this]() {
+        uint64_t seen = 0;
+        while (true) {
+          std::unique_lock<std::mutex> lk(m);
+          cv.wait(lk, [&] { return gen != seen; });
+          seen = gen;
+          lk.unlock();
+          for (int64_t p = next.fetch_add(1); p < npieces; p = next.fetch_add(1)) fn(p);
+          active.fetch_sub(1);
+        }
+      });
+      th.back().detach();  // the pool lives until the process ends
+    }
+  }
+  // starts the job and returns; the workers are busy until active == 0
+  void start(int64_t n, std::function<void(int64_t)> f) {
+    std::lock_guard<std::mutex> lk(m);
+    fn = std::move(f);
+    npieces = n;
+    next.store(0);
+    active.store(static_cast<int>(th.size()));
+    ++gen;
+    cv.notify_all();
+  }
+  void wait() {
+    while (active.load() != 0) std::this_thread::yield();
+  }
+};
+
+int narrow_threads() {
   static const int nt = [] {
     if (const char *s = getenv("CVB_UPLOAD_THREADS")) return atoi(s) > 0 ? atoi(s) : 1;
     const unsigned hw = std::thread::hardware_concurrency();
-    return static_cast<int>(hw >= 32 ? 16 : (hw >= 4 ? hw / 2 : 1));  // CVB_UPLOAD_THREADS overrides
+    const int n = static_cast<int>(hw / 2);  // one per physical core on SMT hosts
+    return n < 1 ? 1 : (n > 64 ? 64 : n);
   }();
-  // Measured on the B200 host (round 2): from PINNED memory the plain 16-byte-per-entry DMA (~50 GB/s)
-  // beats narrowing on the host cores, so the narrow path is taken for pageable sources only (what the
-  // reference's std::vector storage is), where the driver would otherwise stage the copy through its own
-  // bounce buffers.  CVB_NARROW_UPLOAD=1 / 0 forces it on / off.
+  return nt;
+}
+NarrowPool &narrow_pool() {
+  static NarrowPool *pool = new NarrowPool(narrow_threads());  // intentionally never destroyed
+  return *pool;
+}
+}  // namespace
+
+// Host-side narrowing of the boundary arrays (int64 tail + double weight, 16 B per entry) to the device layout
+// (int32 tail, 4 B per entry; uint32 weights only when some weight differs from 1) BEFORE the PCIe transfer: the
+// worker pool converts 256 K-entry pieces into pinned staging, and every finished 4 M-entry chunk goes out with
+// an asynchronous copy while the next ones are converted.  Returns 1 when the graph was uploaded this way, 0 when
+// the caller should use the plain path (real weights, ids beyond int32, no staging memory, small graph).
+static int upload_narrowed(cvb_engine *e, const void *edges_aos, const int64_t *tails, const double *weights,
+                           int64_t ne) {
   if (ne < (1 << 20)) return 0;
   {
+    // Default: pageable sources only (what the reference's std::vector storage is) — there the driver would
+    // stage the 16-byte entries through its own bounce buffers.  CVB_NARROW_UPLOAD=1 / 0 forces it on / off.
     const char *s = getenv("CVB_NARROW_UPLOAD");
     bool want;
     if (s && (s[0] == '0' || s[0] == '1')) {
@@ -1298,53 +1359,54 @@ static int upload_narrowed(cvb_engine *e, const void *edges_aos, const int64_t *
   int32_t *ht = reinterpret_cast<int32_t *>(e->h_stage.p);
   uint32_t *hw = reinterpret_cast<uint32_t *>(e->h_stage.p + static_cast<size_t>(ne) * 4);
   const EdgeAoS *aos = static_cast<const EdgeAoS *>(edges_aos);
-  constexpr int64_t kChunk = int64_t(1) << 22;
-  struct Stat { int bad = 0, nonunit = 0; double sum = 0.0; };
-  std::vector<Stat> stat(nt);
-  for (int64_t c0 = 0; c0 < ne; c0 += kChunk) {
-    const int64_t c1 = c0 + kChunk < ne ? c0 + kChunk : ne;
-    std::vector<std::thread> th;
-    const int64_t per = (c1 - c0 + nt - 1) / nt;
-    for (int t = 0; t < nt; ++t) {
-      const int64_t lo = c0 + t * per, hi = lo + per < c1 ? lo + per : c1;
-      if (lo >= hi) break;
-      th.emplace_back([=, &stat]() {
-        Stat s = stat[t];
-        // branch-free body: range / integrality violations only set bits, sums are exact integers
-        int64_t bad = 0, nonunit = 0;
-        uint64_t sum = 0;
-        for (int64_t i = lo; i < hi; ++i) {
-          const int64_t tl = aos ? aos[i].tail : tails[i];
-          const double w = aos ? aos[i].weight : weights[i];
-          const int64_t wi = static_cast<int64_t>(w);  // NaN / out of range -> INT64_MIN: caught by the range test
-          bad |= (wi >> 32) | (static_cast<double>(wi) != w) | (tl < 0) | (tl > 2147483000LL);
-          nonunit |= wi ^ 1;
-          sum += static_cast<uint64_t>(wi) & 0xffffffffu;
-          ht[i] = static_cast<int32_t>(tl);
-          hw[i] = static_cast<uint32_t>(wi);
-        }
-        s.bad |= bad != 0;
-        s.nonunit |= nonunit != 0;
-        s.sum += static_cast<double>(sum);
-        stat[t] = s;
-      });
+  constexpr int64_t kPiece = int64_t(1) << 18, kPiecesPerChunk = 16;  // DMA granularity: 4 M entries = 16 MB
+  const int64_t npieces = (ne + kPiece - 1) / kPiece;
+  const int64_t nchunks = (npieces + kPiecesPerChunk - 1) / kPiecesPerChunk;
+  struct Stat { std::atomic<int> bad{0}, nonunit{0}; std::atomic<uint64_t> sum{0}; } stat;
+  std::vector<std::atomic<int>> done(nchunks);
+  for (auto &d : done) d.store(0);
+  static std::mutex one_job;  // the pool is process-wide: uploads of several engines take turns
+  std::lock_guard<std::mutex> turn(one_job);
+  NarrowPool &pool = narrow_pool();
+  pool.start(npieces, [=, &stat, &done](int64_t p) {
+    const int64_t lo = p * kPiece, hi = lo + kPiece < ne ? lo + kPiece : ne;
+    // branch-free body: range / integrality violations only set bits, sums are exact integers
+    int64_t bad = 0, nonunit = 0;
+    uint64_t sum = 0;
+    for (int64_t i = lo; i < hi; ++i) {
+      const int64_t tl = aos ? aos[i].tail : tails[i];
+      const double w = aos ? aos[i].weight : weights[i];
+      const int64_t wi = static_cast<int64_t>(w);  // NaN / out of range -> INT64_MIN: caught by the range test
+      bad |= (wi >> 32) | (static_cast<double>(wi) != w) | (tl < 0) | (tl > 2147483000LL);
+      nonunit |= wi ^ 1;
+      sum += static_cast<uint64_t>(wi) & 0xffffffffu;
+      ht[i] = static_cast<int32_t>(tl);
+      hw[i] = static_cast<uint32_t>(wi);
     }
-    for (auto &x : th) x.join();
-    for (int t = 0; t < nt; ++t)
-      if (stat[t].bad) return 0;
+    if (bad) stat.bad.store(1);
+    if (nonunit) stat.nonunit.store(1);
+    stat.sum.fetch_add(sum);
+    done[p / kPiecesPerChunk].fetch_add(1);
+  });
+  bool ok = true;
+  for (int64_t c = 0; c < nchunks && ok; ++c) {
+    const int64_t p0 = c * kPiecesPerChunk, p1 = p0 + kPiecesPerChunk < npieces ? p0 + kPiecesPerChunk : npieces;
+    while (done[c].load() < static_cast<int>(p1 - p0)) std::this_thread::yield();
+    if (stat.bad.load()) { ok = false; break; }
+    const int64_t c0 = p0 * kPiece, c1 = p1 * kPiece < ne ? p1 * kPiece : ne;
     if (cudaMemcpyAsync(e->tails.p + c0, ht + c0, (c1 - c0) * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream) !=
         cudaSuccess)
-      return 0;
+      ok = false;
   }
-  double sum = 0.0;
-  int nonunit = 0;
-  for (int t = 0; t < nt; ++t) {
-    sum += stat[t].sum;
-    nonunit |= stat[t].nonunit;
+  pool.wait();  // the job's captures (stat, done) must outlive the workers' last piece
+  if (!ok || stat.bad.load()) {
+    cudaStreamSynchronize(e->stream);
+    cudaGetLastError();
+    return 0;
   }
-  if (sum >= 4294967296.0) return 0;
+  if (static_cast<double>(stat.sum.load()) >= 4294967296.0) return 0;
   if (e->weights.ensure((static_cast<size_t>(ne) + 1) * 4) != CVB_OK) return 0;
-  if (nonunit) {
+  if (stat.nonunit.load()) {
     if (cudaMemcpyAsync(e->weights.p, hw, ne * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream) != cudaSuccess)
       return 0;
   } else {
@@ -1875,10 +1937,11 @@ static int sort_reduce_pairs(cvb_engine *e, const uint64_t *k_in, const void *w_
   const int64_t mu = nseg32;
   CVB_TRY(ukeys.ensure(mu + 1)); CVB_TRY(uw.ensure((mu + 1) * wbytes)); CVB_TRY(seg_start.ensure(mu + 1));
   k_emit_pairs<<<grid_for(m, 256), 256, 0, st>>>(k_out.p, head.p, seg.p, m, ukeys.p, seg_start.p);
-  if (u32)
-    k_sum_segments_u32<<<static_cast<int>((mu * 32 + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<uint32_t *>(w_out.p), seg_start.p, mu, m, reinterpret_cast<uint32_t *>(uw.p));
-  else
+  if (u32) {
+    CVB_CUDA(cudaMemsetAsync(uw.p, 0, static_cast<size_t>(mu) * sizeof(uint32_t), st));
+    k_sum_segments_u32<<<static_cast<int>((m + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<uint32_t *>(w_out.p), seg.p, m, reinterpret_cast<uint32_t *>(uw.p));
+  } else
     k_sum_segments_f64<<<grid_for(mu, 256), 256, 0, st>>>(reinterpret_cast<double *>(w_out.p), seg_start.p, mu, m,
                                                          reinterpret_cast<double *>(uw.p));
   e->launches += 2;
