@@ -1320,8 +1320,10 @@ int narrow_threads() {
   static const int nt = [] {
     if (const char *s = getenv("CVB_UPLOAD_THREADS")) return atoi(s) > 0 ? atoi(s) : 1;
     const unsigned hw = std::thread::hardware_concurrency();
-    const int n = static_cast<int>(hw / 2);  // one per physical core on SMT hosts
-    return n < 1 ? 1 : (n > 64 ? 64 : n);
+    // measured on the round-2 host (2 x 32 cores, SMT): e2e 3.9 / 4.9 / 2.3 / 1.7 G edges/s with 16 / 32 / 64 /
+    // 128 workers (profiles/r02_e2e_narrowing.txt) — one socket's worth of cores, never more than 32
+    const int n = static_cast<int>(hw / 4);
+    return n < 1 ? 1 : (n > 32 ? 32 : n);
   }();
   return nt;
 }

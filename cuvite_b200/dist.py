@@ -223,12 +223,27 @@ class DistLouvain:
         Returns (newid, nc): newid[i] = new vertex of old GLOBAL vertex i (replicated tensor);
         the all-gathered cvect of the level is left in ``self.last_cvect``."""
         e = self.e
+        stages = getattr(self, "coarsen_seconds", None)
+        if stages is None:
+            stages = self.coarsen_seconds = {}
+        clock = [time.perf_counter()]
+
+        def mark(name):  # CVB_DIST_TIMING=1: per-stage host seconds (with a device sync per stage)
+            if self.timing is not None:
+                torch.cuda.synchronize()
+                now = time.perf_counter()
+                stages[name] = stages.get(name, 0.0) + now - clock[0]
+                clock[0] = now
+
         cv_local = tensor_of(e, "labels_past")
         cv_global = torch.empty(self.nvg, dtype=cv_local.dtype, device=cv_local.device)
         self._all_gather_rows(cv_global, cv_local)
         self.last_cvect = cv_global
+        mark("allgather_cvect")
         newid, nc = e.renumber(cv_global)
+        mark("renumber")
         keys, w = e.contract_local(newid, nc)
+        mark("contract_local")
         parts = partition_ranges(nc, self.world)
         if self.world > 1:
             cuts = torch.tensor(parts[1:-1], dtype=torch.int64, device=keys.device) << 32
@@ -243,11 +258,14 @@ class DistLouvain:
             dist.all_to_all_single(rkeys, keys.contiguous(), recv, send, group=self.group)
             dist.all_to_all_single(rw, w.contiguous(), recv, send, group=self.group)
             keys, w = rkeys, rw
+        mark("all_to_all_pairs")
         e.graph_from_pairs(parts[self.rank + 1] - parts[self.rank], parts[self.rank], nc, keys, w)
+        mark("graph_from_pairs")
         self._set_nv_global(nc)
         if self.native:
             e.dist_set_parts(self.parts)
             e.dist_agree()
+        mark("set_parts_agree")
         return newid, nc
 
     @staticmethod

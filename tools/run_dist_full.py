@@ -60,6 +60,7 @@ def main():
            "n_gpus": world, "nv": nv, "csr_entries": ne, "levels": len(lq), "level_q": lq, "level_iters": li,
            "level_nv": ln, "seconds_max_rank": float(secs.item()),
            "stage_seconds_rank0": dl.seconds, "warmup": not a.no_warmup,
+           "coarsen_stage_seconds_rank0": getattr(dl, "coarsen_seconds", None),
            "communities": int(comm.max().item()) + 1}
     if rank == 0 and not a.no_check:
         one = GpuGraph(stream=side.cuda_stream)
