@@ -238,6 +238,21 @@ struct cvb_engine {
   cudaStream_t S(int k) const { return aux[k % nstreams]; }
 
   DistState dist;  // N > 1: NCCL communicator and vertex ranges (dist.cuh)
+  // coarsening scratch, kept between levels and runs (cudaMalloc / cudaFree of multi-GB buffers per level cost more
+  // than the sorts on a box where 8 processes share the driver; CVB_KEEP_SCRATCH=0 frees it after every call)
+  struct CoarsenScratch {
+    DevBuf<int32_t> first, flag, rank, head, seg, vnew;
+    DevBuf<unsigned char> tmp, w_out, uw;
+    DevBuf<uint64_t> k_in, k_out, ukeys;
+    DevBuf<int64_t> seg_start, noff;
+    DevBuf<unsigned long long> row_count;
+    void release() {
+      first.release(); flag.release(); rank.release(); head.release(); seg.release(); vnew.release(); tmp.release();
+      w_out.release(); uw.release(); k_in.release(); k_out.release(); ukeys.release(); seg_start.release();
+      noff.release(); row_count.release();
+    }
+  } cs;
+  bool keep_scratch = true;
   // colouring (cvb_phase_run_color): per-colour class lists; ovr_* redirect the sweep's class ranges
   DevBuf<int32_t> col_color, col_keys, col_keys2;
   DevBuf<vid_t> col_list, col_ids;
@@ -1195,6 +1210,7 @@ cvb_engine *cvb_create(void *stream) {
   }
   if (const char *s = getenv("CVB_LM_MASK")) e->lm_mask = static_cast<uint32_t>(strtoul(s, nullptr, 0));
   if (const char *s = getenv("CVB_REMAP")) e->use_remap = (s[0] != '0');
+  if (const char *s = getenv("CVB_KEEP_SCRATCH")) e->keep_scratch = (s[0] != '0');
   if (const char *s = getenv("CVB_MP")) e->use_mp = (s[0] == '1');
   if (const char *s = getenv("CVB_BIG")) e->use_big = (s[0] != '0');
   if (const char *s = getenv("CVB_BIG_DENSE")) e->big_dense = (s[0] != '0');
@@ -1244,6 +1260,7 @@ void cvb_destroy(cvb_engine *e) {
   e->partials.release(); e->d_sums.release(); e->ticket.release(); e->d_flags.release();
   e->h_sums.release(); e->staging.release(); e->staging2.release(); e->giant.release(); e->h_stage.release();
   e->packed.release(); e->giant_layout.release(); e->gslots.release(); e->pair_keys.release(); e->pair_w.release();
+  e->cs.release();
   e->col_color.release(); e->col_keys.release(); e->col_keys2.release(); e->col_list.release(); e->col_ids.release();
   e->col_vrec.release(); e->col_bak_t.release(); e->col_bak_cw.release();
   e->cdeg32.release(); e->vrec.release(); e->selfw.release(); e->rank.release(); e->tails_r.release();
@@ -1870,9 +1887,9 @@ int cvb_reduce_mod(cvb_engine *e, int64_t nv, const double *local_cdeg, const do
 // scanning i ascending, of labels[i]'s community.  labels are ids in [0, n).
 static int renumber_impl(cvb_engine *e, const vid_t *labels, int64_t n, int32_t *vnew, int64_t *nnv_out) {
   cudaStream_t st = e->stream;
-  DevBuf<int32_t> first, flag, rank;
-  DevBuf<unsigned char> tmp;
-  auto release = [&]() { first.release(); flag.release(); rank.release(); tmp.release(); };
+  DevBuf<int32_t> &first = e->cs.first, &flag = e->cs.flag, &rank = e->cs.rank;
+  DevBuf<unsigned char> &tmp = e->cs.tmp;
+  auto release = [&]() { if (!e->keep_scratch) { first.release(); flag.release(); rank.release(); tmp.release(); } };
   struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
   *nnv_out = 0;
   if (n == 0) return CVB_OK;
@@ -1906,11 +1923,13 @@ static int sort_reduce_pairs(cvb_engine *e, const uint64_t *k_in, const void *w_
   *mu_out = 0;
   if (m == 0) return CVB_OK;
   CVB_CHECK(m < 2147483000LL, CVB_ERR_CAPACITY, "coarsening: more than 2^31 entries on one GPU");
-  DevBuf<uint64_t> k_out;
-  DevBuf<unsigned char> w_out, tmp;
-  DevBuf<int32_t> head, seg;
-  DevBuf<int64_t> seg_start;
-  auto release = [&]() { k_out.release(); w_out.release(); tmp.release(); head.release(); seg.release(); seg_start.release(); };
+  DevBuf<uint64_t> &k_out = e->cs.k_out;
+  DevBuf<unsigned char> &w_out = e->cs.w_out, &tmp = e->cs.tmp;
+  DevBuf<int32_t> &head = e->cs.head, &seg = e->cs.seg;
+  DevBuf<int64_t> &seg_start = e->cs.seg_start;
+  auto release = [&]() {
+    if (!e->keep_scratch) { k_out.release(); w_out.release(); tmp.release(); head.release(); seg.release(); seg_start.release(); }
+  };
   struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
   size_t tb2 = 0, tb4 = 0;
   if (u32)
@@ -1961,8 +1980,8 @@ static int contract_impl(cvb_engine *e, const int32_t *vnew_global, int64_t nnv,
   *m_out = 0;
   e->pair_count = 0;
   if (ne == 0) return CVB_OK;
-  DevBuf<uint64_t> k_in;
-  struct Guard { DevBuf<uint64_t> &b; ~Guard() { b.release(); } } guard{k_in};
+  DevBuf<uint64_t> &k_in = e->cs.k_in;
+  struct Guard { cvb_engine *e; ~Guard() { if (!e->keep_scratch) e->cs.k_in.release(); } } guard{e};
   CVB_TRY(k_in.ensure(ne));
   k_edge_keys<<<static_cast<int>((nv * 32 + 255) / 256), 256, 0, st>>>(e->offsets.p, e->tails.p, vnew_global, e->base, nv,
                                                                       k_in.p);
@@ -1983,11 +2002,13 @@ static int install_pairs_impl(cvb_engine *e, int64_t nv_local, int64_t base, int
   cudaStream_t st = e->stream;
   const size_t wbytes = e->mode == CVB_WEIGHTS_U32 ? 4 : 8;
   CVB_TRY(check_sizes(nv_local, base, nv_global));
-  DevBuf<uint64_t> ukeys;
-  DevBuf<unsigned char> uw, tmp;
-  DevBuf<unsigned long long> row_count;
-  DevBuf<int64_t> noff;
-  auto release = [&]() { ukeys.release(); uw.release(); tmp.release(); row_count.release(); noff.release(); };
+  DevBuf<uint64_t> &ukeys = e->cs.ukeys;
+  DevBuf<unsigned char> &uw = e->cs.uw, &tmp = e->cs.tmp;
+  DevBuf<unsigned long long> &row_count = e->cs.row_count;
+  DevBuf<int64_t> &noff = e->cs.noff;
+  auto release = [&]() {
+    if (!e->keep_scratch) { ukeys.release(); uw.release(); tmp.release(); row_count.release(); noff.release(); }
+  };
   struct Guard { decltype(release) &f; ~Guard() { f(); } } guard{release};
   int64_t mu = m;
   if (!unique && m > 0) {
@@ -2039,8 +2060,8 @@ static int coarsen_impl(cvb_engine *e, int64_t *new_nv_out, int32_t *d_compose, 
             "cvb_contract_local + cvb_graph_from_pairs)");
   cudaStream_t st = e->stream;
   const int64_t nv = e->nvl;
-  DevBuf<int32_t> vnew;
-  struct Guard { DevBuf<int32_t> &b; ~Guard() { b.release(); } } guard{vnew};
+  DevBuf<int32_t> &vnew = e->cs.vnew;
+  struct Guard { cvb_engine *e; ~Guard() { if (!e->keep_scratch) e->cs.vnew.release(); } } guard{e};
   CVB_TRY(vnew.ensure(nv + 1));
   int64_t nnv = 0, m = 0;
   CVB_TRY(renumber_impl(e, e->lab[e->past].p, nv, vnew.p, &nnv));  // cvect = pastComm, louvain.cpp:741
