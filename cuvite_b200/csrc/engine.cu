@@ -2284,7 +2284,8 @@ int cvb_phase_run_color(cvb_engine *e, double lower, double thresh, int max_colo
   CVB_TRY(color_graph(e, max_colors, &num_colors));
   if (num_colors_out) *num_colors_out = num_colors;
   const int num_color = num_colors + 1;  // main.cpp:259: the last bucket holds the uncoloured vertices
-  if (num_color == 1) return cvb_phase_run(e, lower, thresh, 0, q_out, iters_out);  // louvain.cpp:764-768
+  if (num_color == 1 || e->nvl == 0)  // louvain.cpp:764-768 (and the empty graph: no colour step would run)
+    return cvb_phase_run(e, lower, thresh, 0, q_out, iters_out);
   CVB_TRY(color_lists(e, num_color));
   cudaStream_t st = e->stream;
   const int64_t nvl = e->nvl;

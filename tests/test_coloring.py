@@ -119,3 +119,27 @@ def test_gpu_coloured_phase_on_hub_graph(real_weights):
         assert (q == wq) if not real_weights else abs(q - wq) <= 1e-6
     finally:
         gpu.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ring6x5", "er1k", "rmat10", "rmat10_intw", "rmat9_realw", "hub30k", "empty_rows", "multi9"])
+@pytest.mark.parametrize("max_colors", [8, 2])
+def test_gpu_coloured_phase_on_golden_inputs(name, max_colors):
+    """The edge cases of the golden set under -c: empty rows, repeated tails (multi9), integer weights other
+    than 1 (rmat10_intw), real weights (rmat9_realw, tolerance 1e-6), a 30 k-entry hub."""
+    from conftest import load_golden
+    from cuvite_b200.engine import GpuGraph
+    from oracle.binding import Oracle
+    g = load_golden(name)
+    o, t, w = g["offsets"], g["tails"].astype(np.int64), np.asarray(g["weights"], np.float64)
+    color, n = ce.colour(o, t, max_colors // 2)
+    wq, wit = ce.phase_color(Oracle(), o, t, w, color, n + 1)
+    gpu = GpuGraph()
+    try:
+        gpu.upload(o, t, w)
+        q, it, ncol = gpu.phase_run_color(max_colors)
+        assert ncol == n and np.array_equal(gpu.colors(), color)
+        assert it == wit
+        assert (q == wq) if name != "rmat9_realw" else abs(q - wq) <= 1e-6
+    finally:
+        gpu.close()
