@@ -388,11 +388,13 @@ def bench_multi(args, metric, unit, base_scale, measured_peak_gbs, ClockSampler,
     # AoS, distgraph.hpp) in pinned host memory: the input of the end-to-end leg below
     import numpy as np
     e_lo, e_hi = int(g.offsets[b0]), int(g.offsets[b1])
-    o_pin = torch.from_numpy((g.offsets[b0:b1 + 1] - e_lo).cpu().numpy()).pin_memory().numpy()
+    from .hostmem import near_gpu
     edges = np.empty(e_hi - e_lo, dtype=[("tail", "<i8"), ("weight", "<f8")])
     edges["tail"] = g.tails[e_lo:e_hi].cpu().numpy()
     edges["weight"] = g.weights[e_lo:e_hi].cpu().numpy()
-    edges_pin = torch.from_numpy(edges.view(np.uint8)).pin_memory()
+    with near_gpu(local) as numa_local:  # every rank's pinned rows in the memory of its GPU's socket
+        o_pin = torch.from_numpy((g.offsets[b0:b1 + 1] - e_lo).cpu().numpy()).pin_memory().numpy()
+        edges_pin = torch.from_numpy(edges.view(np.uint8)).pin_memory()
     edges_p = edges_pin.numpy().view(edges.dtype)
     del g, edges
     torch.cuda.empty_cache()
@@ -481,6 +483,7 @@ def bench_multi(args, metric, unit, base_scale, measured_peak_gbs, ClockSampler,
         e2e = {"value": (ne / 2) * res_sweeps / float(secs.item()), "unit": unit, "sweeps": res_sweeps,
                "h2d_bytes_per_step": int(int(h2d.item()) * res_phases / res_sweeps),
                "d2h_bytes_per_step": int(nv * 8 * res_phases / res_sweeps), "phase_q": res_q,
+               "pinned_buffers_numa_local": bool(numa_local),
                "phase_q_equals_device_resident_run": bool(res_q == st["phase_q"]),
                "api": "N-rank distLouvainMethod(.., GpuGraph&) (adapter_resident.cpp): per phase every rank runs "
                       "cvb_graph_upload_host on its rows (pinned AoS) + cvb_dist_set_parts/agree + "
