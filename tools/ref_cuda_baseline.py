@@ -37,6 +37,11 @@ def run_cli(exe, path, threads):
     for name, val in re.findall(r"Time (GPU_\w+): ([0-9.eE+-]+)", out):
         stamps.setdefault(name, []).append(float(val))
     res = {"rc": r.returncode, "wall_s": wall, "levels": levels}
+    phases = re.findall(r"cuvite_b200 resident phase: nv=(\d+) entries=(\d+) upload ([0-9.eE+-]+) s, phase ([0-9.eE+-]+) s "
+                        r"\((\d+) iterations\), labels ([0-9.eE+-]+) s", out)
+    if phases:  # CVB_ADAPTER_TIMING=1: the resident adapter's own split per phase
+        res["resident_phases"] = [{"nv": int(a), "entries": int(b), "upload_s": float(c), "phase_s": float(d),
+                                   "iterations": int(i), "labels_s": float(f)} for a, b, c, d, i, f in phases]
     if "GPU_kernels" in stamps and "GPU_iter1" in stamps:
         k = [a - b for a, b in zip(stamps["GPU_kernels"], stamps["GPU_iter1"])]
         res["kernel_s_per_iteration"] = k
