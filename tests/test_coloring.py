@@ -34,7 +34,7 @@ def _cli(tmp_path, g, max_colors):
 
 
 @pytest.mark.parametrize("graph", ["er3000", "rmat13"])
-@pytest.mark.parametrize("max_colors", [8, 4])
+@pytest.mark.parametrize("max_colors", [8, 4, 16, 3, 32])
 def test_emulation_matches_reference_cli(tmp_path, graph, max_colors):
     """Pins the emulation: number of colours, level-0 modularity (6 digits, as printed) and iterations of
     the reference's own `-c` run."""
@@ -50,7 +50,7 @@ def test_emulation_matches_reference_cli(tmp_path, graph, max_colors):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("graph", ["er3000", "rmat13"])
-@pytest.mark.parametrize("max_colors", [8, 4, 2, 1])
+@pytest.mark.parametrize("max_colors", [8, 4, 2, 1, 16, 3, 32])
 def test_gpu_colouring_and_coloured_phase_match_emulation(graph, max_colors):
     """Colours bit for bit, number of colours, and the coloured phase (modularity EXACTLY — unit weights make
     every sum an integer — and iterations) against the CPU emulation."""
