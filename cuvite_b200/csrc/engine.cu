@@ -263,6 +263,7 @@ struct cvb_engine {
   std::vector<int64_t> col_start;        // [col_num * kNumClasses + 1] start of every (colour, class) range in col_list
   bool ovr = false;                      // a colour step: classes below kClsC2 come from col_list / col_vrec
   bool ovr_big = false;                  // ... and this colour has vertices above 8192 entries
+  bool ovr_et = false;                   // ... with early termination (frozen vertices keep target / clusterWeight)
   int ovr_color = 0;
   // early termination (cvb_phase_run_et)
   bool et_no_deltas = false;
@@ -697,7 +698,7 @@ int launch_sweep_u32(cvb_engine *e) {
       k_color_fix_big<<<static_cast<int>((n + 127) / 128), 128, 0, e->S(1)>>>(
           e->list.p + e->class_start[kClsC2], static_cast<int>(n), e->col_color.p, e->col_num, e->ovr_color,
           e->lab[e->targ].p, e->lab[e->curr].p, e->cw.p, e->col_bak_t.p, e->col_bak_cw.p, e->vdeg.p, e->ddeg.p,
-          e->dsize.p);
+          e->dsize.p, e->ovr_et ? e->et_active.p : nullptr, e->et_frozen_target.p, e->et_frozen_cw.p);
       e->launches++;
     }
   }
@@ -2300,13 +2301,26 @@ static int color_lists(cvb_engine *e, int num_color) {
 // the (colour, class) ranges of the per-colour lists.
 int cvb_phase_run_color(cvb_engine *e, double lower, double thresh, int max_colors, double *q_out, int *iters_out,
                         int *num_colors_out) {
+  return cvb_phase_run_color_et(e, lower, thresh, max_colors, 0, 1.0, q_out, iters_out, num_colors_out);
+}
+
+// et_type 0: louvain.cpp:756-949.  et_type 1 / 3: louvain.cpp:951-1178, et_type 2 / 4: louvain.cpp:1180-1426 — the
+// coloured phase with the per-vertex freezing of cvb_phase_run_et: every kernel of a colour step runs with the
+// delta atomics off, k_et_fix_list / k_color_fix_big add the moves of the ACTIVE vertices of the colour and give the
+// frozen ones their frozen target / clusterWeight back; labels rotate per vertex (k_et_rotate).
+int cvb_phase_run_color_et(cvb_engine *e, double lower, double thresh, int max_colors, int et_type, double et_delta,
+                           double *q_out, int *iters_out, int *num_colors_out) {
   CVB_CHECK(e && e->graph_ready, CVB_ERR_STATE, "cvb_phase_run_color: no graph uploaded");
   CVB_CHECK(e->nvl == e->nvg, CVB_ERR_STATE, "cvb_phase_run_color is the one-GPU driver");
+  CVB_CHECK(et_type >= 0 && et_type <= 4, CVB_ERR_ARG, "early-termination type must be 0..4 (option -t)");
+  CVB_CHECK(!(et_type == 2 || et_type == 4) || (et_delta >= 0.0 && et_delta <= 1.0), CVB_ERR_ARG,
+            "early-termination delta must be in [0, 1] (option -a)");
+  const bool et = et_type != 0, prob = et_type == 2 || et_type == 4, cutoff = et_type == 3 || et_type == 4;
   int num_colors = 0;
   CVB_TRY(color_graph(e, max_colors, &num_colors));
   if (num_colors_out) *num_colors_out = num_colors;
   const int num_color = num_colors + 1;  // main.cpp:259: the last bucket holds the uncoloured vertices
-  if (num_color == 1 || e->nvl == 0)  // louvain.cpp:764-768 (and the empty graph: no colour step would run)
+  if (num_color == 1 || e->nvl == 0)  // louvain.cpp:764-768, 958-962 (and the empty graph: no colour step would run)
     return cvb_phase_run(e, lower, thresh, 0, q_out, iters_out);
   CVB_TRY(color_lists(e, num_color));
   cudaStream_t st = e->stream;
@@ -2318,9 +2332,26 @@ int cvb_phase_run_color(cvb_engine *e, double lower, double thresh, int max_colo
     CVB_TRY(e->col_bak_cw.ensure(nbig));
   }
   CVB_TRY(cvb_phase_begin(e, 0.0));
-  struct Restore { cvb_engine *e; ~Restore() { e->ovr = false; } } restore{e};
+  if (et) {
+    CVB_TRY(e->et_active.ensure(nvl + 1));
+    CVB_TRY(e->et_frozen_target.ensure(nvl + 1));
+    CVB_TRY(e->et_frozen_cw.ensure(nvl + 1));
+    CVB_TRY(e->et_count.ensure(4));
+    CVB_CUDA(cudaMemsetAsync(e->et_active.p, 1, nvl + 1, st));
+    CVB_CUDA(cudaMemsetAsync(e->et_frozen_cw.p, 0, (nvl + 1) * sizeof(double), st));
+    CVB_CUDA(cudaMemsetAsync(e->et_count.p, 0, 4 * sizeof(unsigned int), st));
+    if (prob) {
+      for (auto &b : e->et_p) CVB_TRY(b.ensure(nvl + 1));
+      k_fill_f64<<<grid_for(nvl, 256), 256, 0, st>>>(e->et_p[0].p, nvl, 1.0);  // p_prev = 1
+      CVB_CUDA(cudaMemsetAsync(e->et_p[1].p, 0, nvl * sizeof(double), st));
+    }
+  }
+  struct Restore { cvb_engine *e; ~Restore() { e->ovr = false; e->ovr_et = false; e->et_no_deltas = false; } } restore{e};
+  e->ovr_et = et;
+  e->et_no_deltas = et;
   double prev = lower, cur = -1.0;
-  int iters = 0;
+  int iters = 0, pp = 0;
+  unsigned int frozen = 0;  // vc_count of the iteration about to run = vertices frozen so far
   while (true) {
     iters++;
     CVB_CUDA(cudaMemsetAsync(e->cw.p, 0, nvl * sizeof(double), st));  // louvain.cpp:857-858
@@ -2339,17 +2370,41 @@ int cvb_phase_run_color(cvb_engine *e, double lower, double thresh, int max_colo
       const int rc = cvb_sweep(e);
       e->ovr = false;
       CVB_TRY(rc);
+      if (et) {  // the listed vertices of the colour (U32 mode: the big ones are handled by k_color_fix_big)
+        const int64_t n = (e->mode == CVB_WEIGHTS_U32 ? cs[kClsC2] : cs[kNumClasses]) - cs[0];
+        if (n > 0) {
+          k_et_fix_list<<<grid_for(n, 256), 256, 0, st>>>(e->col_list.p + cs[0], n, e->et_active.p, e->lab[e->targ].p,
+                                                         e->lab[e->curr].p, e->et_frozen_target.p, e->cw.p,
+                                                         e->et_frozen_cw.p, e->vdeg.p, e->ddeg.p, e->dsize.p);
+          e->launches++;
+        }
+      }
       CVB_TRY(apply_reduce_async(e));  // louvain.cpp:887-893; the sums of the last colour are the iteration's
     }
     CVB_CUDA(cudaStreamSynchronize(st));
     double sums[3];
     memcpy(sums, e->h_sums.p, sizeof sums);
     CVB_CHECK(sums[2] == 0.0, CVB_ERR_CAPACITY, "a partition bucket of the big-vertex path overflowed; rerun with CVB_BIG=0");
+    if (cutoff && frozen >= 90u) {  // ET_CUTOFF; louvain.cpp:1131-1138 (here AFTER the community updates of the colours)
+      cur = -1.0;
+      break;
+    }
     cur = cvb_modularity_from_sums(e, sums);
     if ((cur - prev) < thresh) break;
     prev = cur;
     if (prev < lower) prev = lower;
-    CVB_TRY(cvb_rotate_labels(e));
+    if (!et) {
+      CVB_TRY(cvb_rotate_labels(e));
+      continue;
+    }
+    k_et_rotate<<<grid_for(nvl, 256), 256, 0, st>>>(nvl, iters, prob ? 1 : 0, 1.0 - et_delta, e->lab[e->past].p,
+                                                    e->lab[e->curr].p, e->lab[e->targ].p, e->et_active.p,
+                                                    e->et_frozen_target.p, prob ? e->et_p[pp].p : nullptr,
+                                                    prob ? e->et_p[pp ^ 1].p : nullptr, e->et_count.p);
+    e->launches++;
+    pp ^= 1;
+    CVB_CUDA(cudaMemcpyAsync(&frozen, e->et_count.p, sizeof frozen, cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(cudaStreamSynchronize(st));
   }
   if (q_out) *q_out = prev;
   if (iters_out) *iters_out = iters;
@@ -2372,6 +2427,11 @@ int cvb_louvain_run_et(cvb_engine *e, int max_levels, int flags, int et_type, do
 int cvb_louvain_run_color(cvb_engine *e, int max_levels, int flags, int max_colors, double *level_q,
                           int *level_iters, int64_t *level_nv, int64_t *comm_out) {
   return louvain_run_impl(e, max_levels, flags, 0, 1.0, max_colors, level_q, level_iters, level_nv, comm_out);
+}
+
+int cvb_louvain_run_color_et(cvb_engine *e, int max_levels, int flags, int max_colors, int et_type, double et_delta,
+                             double *level_q, int *level_iters, int64_t *level_nv, int64_t *comm_out) {
+  return louvain_run_impl(e, max_levels, flags, et_type, et_delta, max_colors, level_q, level_iters, level_nv, comm_out);
 }
 
 static int louvain_run_impl(cvb_engine *e, int max_levels, int flags, int et_type, double et_delta, int max_colors,
@@ -2398,7 +2458,7 @@ static int louvain_run_impl(cvb_engine *e, int max_levels, int flags, int et_typ
       threshold = sp <= 2 ? 1.0e-3 : sp <= 6 ? 1.0e-4 : sp <= 9 ? 1.0e-5 : 1.0e-6;
     }
     int rc = (max_colors >= 0 && phase == 0)  // option -c: the first phase only, main.cpp:242-282
-                 ? cvb_phase_run_color(e, curr, threshold, max_colors, &curr, &iters, nullptr)
+                 ? cvb_phase_run_color_et(e, curr, threshold, max_colors, et_type, et_delta, &curr, &iters, nullptr)
                  : et_type ? cvb_phase_run_et(e, curr, threshold, et_type, et_delta, &curr, &iters)  // main.cpp:326-341
                            : cvb_phase_run(e, curr, threshold, 0, &curr, &iters);                    // main.cpp:344
     if (rc != CVB_OK) return rc;

@@ -478,6 +478,32 @@ __global__ void k_et_fix(int64_t nvl, const unsigned char *__restrict__ active, 
   }
 }
 
+// The same over a vertex list (a colour step of the coloured phase with early termination, louvain.cpp:1086-1098).
+__global__ void k_et_fix_list(const vid_t *__restrict__ list, int64_t n, const unsigned char *__restrict__ active,
+                              vid_t *__restrict__ target, const vid_t *__restrict__ curr,
+                              const vid_t *__restrict__ frozen_target, double *__restrict__ cw,
+                              double *__restrict__ frozen_cw, const double *__restrict__ vdeg,
+                              double *__restrict__ ddeg, int32_t *__restrict__ dsize) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const vid_t v = list[i];
+    if (!active[v]) {
+      target[v] = frozen_target[v];
+      cw[v] = frozen_cw[v];
+    } else {
+      frozen_cw[v] = cw[v];
+      const vid_t t = target[v], c = curr[v];
+      if (t != c) {
+        const double d = vdeg[v];
+        atomicAdd(&ddeg[t], d);
+        atomicAdd(&dsize[t], 1);
+        atomicAdd(&ddeg[c], -d);
+        atomicAdd(&dsize[c], -1);
+      }
+    }
+  }
+}
+
 // The per-vertex label rotation with the freeze rules, bug for bug:
 //   types 1, 3 (louvain.cpp:174-186): EVERY vertex, frozen or not, either freezes — when
 //     numIters > 2 and `targetComm[i] == currComm[i] == pastComm[i]`, which C++ parses as
@@ -606,15 +632,27 @@ __global__ void k_key_histogram(const int32_t *__restrict__ keys, int64_t n, uns
 // Big vertices (above 8192 entries) in a colour step: their kernels ran over ALL of them with the delta
 // atomics off; vertices of the current colour keep the result and contribute their move, the others get
 // the values of their own colour step (or of the start of the iteration) back.
+// With early termination (active != nullptr) a frozen vertex of the colour takes its frozen target / clusterWeight
+// and moves nothing; an active one records the new clusterWeight as the frozen one.
 __global__ void k_color_fix_big(const vid_t *__restrict__ big_list, int nbig, const int32_t *__restrict__ color,
                                 int num_color, int ci, vid_t *__restrict__ target, const vid_t *__restrict__ curr,
                                 double *__restrict__ cw, vid_t *__restrict__ bak_t, double *__restrict__ bak_cw,
-                                const double *__restrict__ vdeg, double *__restrict__ ddeg, int32_t *__restrict__ dsize) {
+                                const double *__restrict__ vdeg, double *__restrict__ ddeg, int32_t *__restrict__ dsize,
+                                const unsigned char *__restrict__ active, const vid_t *__restrict__ frozen_target,
+                                double *__restrict__ frozen_cw) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nbig) return;
   const vid_t v = big_list[i];
   const int b = color[v] < 0 ? num_color - 1 : color[v];
   if (b == ci) {
+    if (active && !active[v]) {
+      target[v] = frozen_target[v];
+      cw[v] = frozen_cw[v];
+      bak_t[i] = target[v];
+      bak_cw[i] = cw[v];
+      return;
+    }
+    if (active) frozen_cw[v] = cw[v];
     bak_t[i] = target[v];
     bak_cw[i] = cw[v];
     const vid_t t = target[v], c = curr[v];

@@ -217,12 +217,14 @@ class GpuGraph:
         check(self._L.cvb_phase_run_et(self._h, lower, thresh, et_type, et_delta, C.byref(q), C.byref(it)), "phase_run_et")
         return q.value, it.value
 
-    def phase_run_color(self, max_colors: int, lower: float = -1.0, thresh: float = 1e-6):
-        """cvb_phase_run_color: colouring (option -c max_colors) + the coloured phase.  Returns
-        (Q, iterations, number of colours as the reference prints it)."""
+    def phase_run_color(self, max_colors: int, lower: float = -1.0, thresh: float = 1e-6, et_type: int = 0,
+                        et_delta: float = 1.0):
+        """cvb_phase_run_color[_et]: colouring (option -c max_colors) + the coloured phase, optionally with early
+        termination (-t et_type, -a et_delta).  Returns (Q, iterations, number of colours as the reference
+        prints it)."""
         q, it, nc = C.c_double(0), C.c_int(0), C.c_int(0)
-        check(self._L.cvb_phase_run_color(self._h, lower, thresh, max_colors, C.byref(q), C.byref(it), C.byref(nc)),
-              "phase_run_color")
+        check(self._L.cvb_phase_run_color_et(self._h, lower, thresh, max_colors, et_type, et_delta, C.byref(q),
+                                             C.byref(it), C.byref(nc)), "phase_run_color")
         return q.value, it.value, nc.value
 
     def colors(self) -> np.ndarray:
@@ -234,17 +236,15 @@ class GpuGraph:
     def run(self, max_levels: int = 200, threshold_cycling: bool = False, et_type: int = 0, et_delta: float = 1.0,
             max_colors: int | None = None):
         """cvb_louvain_run[_ex/_et/_color]: the phase loop of main.cpp:218-495 (threshold_cycling = option -i,
-        et_type / et_delta = options -t / -a, max_colors = option -c; -c and -t are not combined)."""
+        et_type / et_delta = options -t / -a, max_colors = option -c)."""
         nv0 = self.info().nv_local
         lq = np.zeros(max_levels)
         li = np.zeros(max_levels, np.int32)
         ln = np.zeros(max_levels, np.int64)
         comm = np.empty(nv0, np.int64)
         if max_colors is not None:
-            if et_type:
-                raise ValueError("colouring (-c) with early termination (-t) is not implemented")
-            n = self._L.cvb_louvain_run_color(self._h, max_levels, 1 if threshold_cycling else 0, max_colors,
-                                              _ptr(lq), _ptr(li), _ptr(ln), _ptr(comm))
+            n = self._L.cvb_louvain_run_color_et(self._h, max_levels, 1 if threshold_cycling else 0, max_colors,
+                                                 et_type, et_delta, _ptr(lq), _ptr(li), _ptr(ln), _ptr(comm))
         else:
             n = self._L.cvb_louvain_run_et(self._h, max_levels, 1 if threshold_cycling else 0, et_type, et_delta,
                                            _ptr(lq), _ptr(li), _ptr(ln), _ptr(comm))

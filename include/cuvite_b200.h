@@ -303,12 +303,19 @@ int cvb_louvain_run_et(cvb_engine *e, int max_levels, int flags, int et_type, do
  * distLouvainMethodWithColoring (louvain.cpp:756-949) — inside an iteration the colour buckets are swept
  * one after the other against the community info the earlier buckets left.  *num_colors_out = the
  * reference's "Number of colors (2*nHash)".  max_colors < 2 runs the plain phase, as the reference does.
- * One GPU; not combined with early termination. */
+ * One GPU. */
 int cvb_phase_run_color(cvb_engine *e, double lower, double thresh, int max_colors, double *q_out,
                         int *iters_out, int *num_colors_out);
 /* cvb_louvain_run_ex with the FIRST phase run by cvb_phase_run_color (the reference colours phase 0 only). */
 int cvb_louvain_run_color(cvb_engine *e, int max_levels, int flags, int max_colors, double *level_q,
                           int *level_iters, int64_t *level_nv, int64_t *comm_out);
+/* -c together with -t / -a (main.cpp:258-277): the coloured phase with early termination, louvain.cpp:951-1178
+ * (et_type 1, 3) and 1180-1426 (et_type 2, 4); et_type 0 = cvb_phase_run_color.  In cvb_louvain_run_color_et the
+ * first phase is coloured with early termination and the later ones run cvb_phase_run_et, as main.cpp does. */
+int cvb_phase_run_color_et(cvb_engine *e, double lower, double thresh, int max_colors, int et_type, double et_delta,
+                           double *q_out, int *iters_out, int *num_colors_out);
+int cvb_louvain_run_color_et(cvb_engine *e, int max_levels, int flags, int max_colors, int et_type, double et_delta,
+                             double *level_q, int *level_iters, int64_t *level_nv, int64_t *comm_out);
 /* The colours of the last cvb_phase_run_color (-1 = uncoloured), nv_local values. */
 int cvb_get_colors(cvb_engine *e, int32_t *out);
 

@@ -83,3 +83,63 @@ def phase_color(orc, o, t, w, color, numcolor, lower=-1.0, thresh=1e-6):
         prev = max(q, lower)
         past, curr, target = curr, target.copy(), past.copy()
     return prev, iters
+
+
+def phase_color_et(orc, o, t, w, color, numcolor, et_type, delta, lower=-1.0, thresh=1e-6):
+    """distLouvainMethodWithColoring with early termination: louvain.cpp:951-1178 (et_type 1, 3) and 1180-1426
+    (et_type 2, 4), freeze rules as written there (incl. `target == curr == past` and the never-initialised p_curr)."""
+    prob, cutoff = et_type in (2, 4), et_type in (3, 4)
+    nv = o.size - 1
+    vdeg = orc.vertex_degree(o, w)
+    const = 1.0 / vdeg.sum()
+    past = np.arange(nv)
+    curr = np.arange(nv)
+    target = np.zeros(nv, np.int64)
+    cdeg = vdeg.copy()
+    csize = np.ones(nv, np.int64)
+    bucket = np.where(color < 0, numcolor - 1, color)
+    active = np.ones(nv, bool)
+    frozen_cw = np.zeros(nv)
+    p_prev, p_curr = np.ones(nv), np.zeros(nv)
+    prev, iters = lower, 0
+    while True:
+        iters += 1
+        cw = np.zeros(nv)
+        vc = 0
+        for ci in range(numcolor):
+            sel = bucket == ci
+            if not sel.any():
+                continue
+            tg, cwv, _, _ = orc.sweep(nv, 0, nv, o, t, w, curr, vdeg, cdeg, csize, const)
+            a, f = sel & active, sel & ~active
+            cw[f] = frozen_cw[f]
+            vc += int(f.sum())
+            target[a] = tg[a]
+            cw[a] = cwv[a]
+            frozen_cw[a] = cwv[a]
+            mv = a & (tg != curr)
+            np.add.at(cdeg, tg[mv], vdeg[mv])
+            np.add.at(cdeg, curr[mv], -vdeg[mv])
+            np.add.at(csize, tg[mv], 1)
+            np.add.at(csize, curr[mv], -1)
+        if cutoff and vc >= 90:
+            break
+        q, _ = orc.modularity(cw, cdeg, const)
+        if q - prev < thresh:
+            break
+        prev = max(q, lower)
+        if not prob:
+            freeze = (iters > 2) & ((target == curr).astype(np.int64) == past)
+            active[freeze] = False
+            rot = ~freeze
+        else:
+            hit = active & (iters > 2) & (curr == past)
+            p_curr[hit] = p_prev[hit] * (1.0 - delta)
+            active[hit & (p_curr <= 0.02)] = False
+            rot = active.copy()
+        tmp = past[rot].copy()
+        past[rot] = curr[rot]
+        curr[rot] = target[rot]
+        target[rot] = tmp
+        p_curr, p_prev = p_prev, p_curr
+    return prev, iters

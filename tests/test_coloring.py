@@ -143,3 +143,80 @@ def test_gpu_coloured_phase_on_golden_inputs(name, max_colors):
         assert (q == wq) if name != "rmat9_realw" else abs(q - wq) <= 1e-6
     finally:
         gpu.close()
+
+
+# ---- -c together with -t / -a (louvain.cpp:951-1426) ---------------------------------------------------------
+ET_CASES = [(1, 1.0), (3, 1.0), (2, 0.9), (4, 0.9), (2, 0.25)]
+
+
+def _cli_et(tmp_path, g, max_colors, et_type, delta):
+    """The reference CLI with -c and -t [-a], ONE host thread (its vector<bool> freeze mask races otherwise)."""
+    from cuvite_b200 import vite_io
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/gc_cpu64 not built (needs /root/reference at build time)")
+    f = str(tmp_path / "g.bin")
+    vite_io.write_vite(f, g)
+    opts = ["-c", str(max_colors), "-t", str(et_type)] + (["-a", str(delta)] if et_type in (2, 4) else [])
+    r = subprocess.run([EXE, "-f", f] + opts, capture_output=True, text=True, timeout=600, cwd=str(tmp_path),
+                       env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    levels = re.findall(r"Level \d+, Modularity: ([0-9.eE+-]+), Clustering time: [^,]*, Iterations: (\d+)", r.stdout)
+    assert levels
+    return [(float(q), int(i)) for q, i in levels]
+
+
+@pytest.mark.parametrize("graph", ["er3000", "rmat13"])
+@pytest.mark.parametrize("et_type,delta", ET_CASES)
+def test_emulation_with_early_termination_matches_reference_cli(tmp_path, graph, et_type, delta):
+    from oracle.binding import Oracle
+    g = _graph(graph)
+    o, t, w = g.offsets.numpy(), g.tails.numpy(), g.weights.numpy().astype(np.float64)
+    levels = _cli_et(tmp_path, g, 8, et_type, delta)
+    color, n = ce.colour(o, t, 4)
+    q, it = ce.phase_color_et(Oracle(), o, t, w, color, n + 1, et_type, delta)
+    assert f"{q:.6g}" == f"{levels[0][0]:.6g}" and it == levels[0][1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", ["er3000", "rmat13", "hub"])
+@pytest.mark.parametrize("et_type,delta", ET_CASES)
+def test_gpu_coloured_phase_with_early_termination_matches_emulation(graph, et_type, delta):
+    """cvb_phase_run_color_et against the emulation: modularity exactly, iterations — incl. the hub graph, whose
+    vertices above 8192 entries go through k_color_fix_big's frozen / active handling."""
+    from cuvite_b200.engine import GpuGraph
+    from oracle.binding import Oracle
+    if graph == "hub":
+        from graphs import hub_graph
+        o, t, w = (np.asarray(x) for x in hub_graph())
+        w = w.astype(np.float64)
+    else:
+        g = _graph(graph)
+        o, t, w = g.offsets.numpy(), g.tails.numpy(), g.weights.numpy().astype(np.float64)
+    color, n = ce.colour(o, t, 4)
+    wq, wit = ce.phase_color_et(Oracle(), o, t, w, color, n + 1, et_type, delta)
+    gpu = GpuGraph()
+    try:
+        gpu.upload(o, t, w)
+        q, it, ncol = gpu.phase_run_color(8, et_type=et_type, et_delta=delta)
+        assert ncol == n and (q, it) == (wq, wit)
+    finally:
+        gpu.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", ["er3000", "rmat13"])
+@pytest.mark.parametrize("et_type,delta", ET_CASES)
+def test_gpu_full_run_with_colouring_and_early_termination_matches_reference_cli(tmp_path, graph, et_type, delta):
+    """cvb_louvain_run_color_et == the reference CLI with -c 8 -t k [-a d]: phase 0 coloured with early termination,
+    later phases with early termination only (main.cpp:242-341)."""
+    from cuvite_b200.engine import GpuGraph
+    g = _graph(graph)
+    levels = _cli_et(tmp_path, g, 8, et_type, delta)
+    gpu = GpuGraph()
+    try:
+        gpu.upload(g.offsets.numpy(), g.tails.numpy(), g.weights.numpy())
+        lq, li, _, _ = gpu.run(max_colors=8, et_type=et_type, et_delta=delta)
+    finally:
+        gpu.close()
+    assert [f"{q:.6g}" for q in lq] == [f"{q:.6g}" for q, _ in levels]
+    assert li == [i for _, i in levels]
