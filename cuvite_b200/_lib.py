@@ -73,6 +73,7 @@ SIGNATURES = {
     "cvb_phase_run_color_et": (_i32, [_vp, _f64, _f64, _i32, _i32, _f64, C.POINTER(_f64), C.POINTER(_i32),
                                       C.POINTER(_i32)]),
     "cvb_louvain_run_color_et": (_i32, [_vp, _i32, _i32, _i32, _i32, _f64, _vp, _vp, _vp, _vp]),
+    "cvb_color_graph": (_i32, [_vp, _i32, C.POINTER(_i32)]),
     "cvb_get_colors": (_i32, [_vp, _vp]),
     "cvb_dist_unique_id": (_i32, [_vp, _i32]),
     "cvb_dist_init": (_i32, [_vp, _vp, _i32, _i32, _i32]),

@@ -2299,6 +2299,12 @@ static int color_lists(cvb_engine *e, int num_color) {
 // community info as the earlier colours of the same iteration left it (louvain.cpp:864-899); the new labels
 // take effect together at the end of the iteration.  The sweep kernels are the ordinary ones, launched over
 // the (colour, class) ranges of the per-colour lists.
+int cvb_color_graph(cvb_engine *e, int max_colors, int *num_colors_out) {
+  CVB_CHECK(e && e->graph_ready && num_colors_out, CVB_ERR_STATE, "cvb_color_graph: no graph uploaded");
+  CVB_CHECK(e->nvl == e->nvg, CVB_ERR_STATE, "cvb_color_graph is the one-GPU colouring");
+  return color_graph(e, max_colors, num_colors_out);
+}
+
 int cvb_phase_run_color(cvb_engine *e, double lower, double thresh, int max_colors, double *q_out, int *iters_out,
                         int *num_colors_out) {
   return cvb_phase_run_color_et(e, lower, thresh, max_colors, 0, 1.0, q_out, iters_out, num_colors_out);

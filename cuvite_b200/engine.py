@@ -227,6 +227,13 @@ class GpuGraph:
                                              C.byref(it), C.byref(nc)), "phase_run_color")
         return q.value, it.value, nc.value
 
+    def color_graph(self, max_colors: int) -> int:
+        """cvb_color_graph: the colouring alone (what option -d adds to the plain phase on one rank).  Returns the
+        number of colours as the reference prints it."""
+        nc = C.c_int(0)
+        check(self._L.cvb_color_graph(self._h, max_colors, C.byref(nc)), "color_graph")
+        return nc.value
+
     def colors(self) -> np.ndarray:
         """cvb_get_colors: the colours of the last coloured phase (-1 = uncoloured)."""
         out = np.empty(self.info().nv_local, np.int32)

@@ -316,7 +316,15 @@ int cvb_phase_run_color_et(cvb_engine *e, double lower, double thresh, int max_c
                            double *q_out, int *iters_out, int *num_colors_out);
 int cvb_louvain_run_color_et(cvb_engine *e, int max_levels, int flags, int max_colors, int et_type, double et_delta,
                              double *level_q, int *level_iters, int64_t *level_nv, int64_t *comm_out);
-/* The colours of the last cvb_phase_run_color (-1 = uncoloured), nv_local values. */
+/* distColoringMultiHashMinMax alone (coloring.cpp:3-72): colours the uploaded graph, *num_colors_out = the
+ * reference's "Number of colors (2*nHash)"; read the colours with cvb_get_colors.  This is all option -d
+ * (vertex ordering, main.cpp:283-324, louvain.cpp:1433-1625) adds on one rank: distLouvainMethodVertexOrder visits
+ * the vertices colour by colour but applies the community updates once per iteration, so every vertex still reads
+ * the iteration's starting state and the phase equals cvb_phase_run exactly — likewise `-d` with `-t` equals
+ * cvb_phase_run_et (tests/test_coloring.py pins this on the reference CLI: `-d 8` prints the plain run's level
+ * lines). */
+int cvb_color_graph(cvb_engine *e, int max_colors, int *num_colors_out);
+/* The colours of the last cvb_phase_run_color / cvb_color_graph (-1 = uncoloured), nv_local values. */
 int cvb_get_colors(cvb_engine *e, int32_t *out);
 
 /* ---- instrumentation ------------------------------------------------------ */

@@ -220,3 +220,49 @@ def test_gpu_full_run_with_colouring_and_early_termination_matches_reference_cli
         gpu.close()
     assert [f"{q:.6g}" for q in lq] == [f"{q:.6g}" for q, _ in levels]
     assert li == [i for _, i in levels]
+
+
+# ---- option -d (vertex ordering) -----------------------------------------------------------------------------
+def _cli_plain(tmp_path, g, opts):
+    from cuvite_b200 import vite_io
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/gc_cpu64 not built (needs /root/reference at build time)")
+    f = str(tmp_path / "g.bin")
+    vite_io.write_vite(f, g)
+    r = subprocess.run([EXE, "-f", f] + opts, capture_output=True, text=True, timeout=600, cwd=str(tmp_path),
+                       env=dict(os.environ, OMP_NUM_THREADS="4"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ncol = re.search(r"Number of colors \(2\*nHash\): (\d+)", r.stdout)
+    levels = re.findall(r"Level \d+, Modularity: ([0-9.eE+-]+), Clustering time: [^,]*, Iterations: (\d+)", r.stdout)
+    return (int(ncol.group(1)) if ncol else None), [(q, int(i)) for q, i in levels]
+
+
+@pytest.mark.parametrize("graph", ["er3000", "rmat13"])
+def test_reference_vertex_ordering_equals_plain_run(tmp_path, graph):
+    """Pins the claim in include/cuvite_b200.h: on one rank `-d 8` prints the level lines of the plain run (the
+    colour-ordered visit applies the community updates once per iteration), plus the number of colours."""
+    g = _graph(graph)
+    ncol, with_d = _cli_plain(tmp_path, g, ["-d", "8"])
+    _, plain = _cli_plain(tmp_path, g, [])
+    assert with_d == plain and ncol is not None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", ["er3000", "rmat13"])
+def test_gpu_vertex_ordering_is_colouring_plus_plain_run(tmp_path, graph):
+    """Option -d on the GPU: cvb_color_graph gives the CLI's number of colours (and the emulation's colours), the
+    run itself is cvb_louvain_run — equal to the CLI's `-d 8` level lines."""
+    from cuvite_b200.engine import GpuGraph
+    g = _graph(graph)
+    ncol, levels = _cli_plain(tmp_path, g, ["-d", "8"])
+    color, n = ce.colour(g.offsets.numpy(), g.tails.numpy(), 4)
+    gpu = GpuGraph()
+    try:
+        gpu.upload(g.offsets.numpy(), g.tails.numpy(), g.weights.numpy())
+        assert gpu.color_graph(8) == ncol == n
+        assert np.array_equal(gpu.colors(), color)
+        lq, li, _, _ = gpu.run()
+    finally:
+        gpu.close()
+    assert [f"{q:.6g}" for q in lq] == [f"{float(q):.6g}" for q, _ in levels]
+    assert li == [i for _, i in levels]
