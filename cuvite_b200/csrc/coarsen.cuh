@@ -95,17 +95,31 @@ __global__ void k_emit_pairs(const uint64_t *__restrict__ keys, const int32_t *_
 
 // Distinct ascending pairs -> CSR pieces: tails[s] = dst, row_count[src - base]++.
 // A source outside [base, base + nv_local) raises *bad (the caller routed a pair wrongly).
+// One thread per pair (the grid covers m exactly once).  The pairs ascend by source, so the pairs of a row are
+// contiguous: a warp counts its runs with one ballot and only the first lane of a run issues the atomic — one per
+// row and warp instead of one per pair (hub rows of a coarsened graph hold millions of pairs).
 __global__ void k_pairs_to_rows(const uint64_t *__restrict__ ukeys, int64_t m, int64_t base, int64_t nv_local,
                                 vid_t *__restrict__ ntails, unsigned long long *__restrict__ row_count,
                                 int *__restrict__ bad) {
-  for (int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; s < m;
-       s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t row = static_cast<int64_t>(ukeys[s] >> 32) - base;
-    ntails[s] = static_cast<vid_t>(ukeys[s] & 0xFFFFFFFFull);
-    if (row < 0 || row >= nv_local)
+  const int64_t s = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  int64_t row = -2;  // beyond the last pair: a run of its own, never counted
+  if (s < m) {
+    const uint64_t k = ukeys[s];
+    row = static_cast<int64_t>(k >> 32) - base;
+    ntails[s] = static_cast<vid_t>(k & 0xFFFFFFFFull);
+    if (row < 0 || row >= nv_local) {
       *bad = 1;
-    else
-      atomicAdd(&row_count[row], 1ull);
+      row = -1;
+    }
+  }
+  const int64_t prev = __shfl_up_sync(0xffffffffu, row, 1);
+  const bool head = lane == 0 || prev != row;
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  if (head && row >= 0) {
+    const unsigned above = heads & ~((2u << lane) - 1u);  // heads after this lane (lane 31: none)
+    const int next = above ? __ffs(above) - 1 : 32;
+    atomicAdd(&row_count[row], static_cast<unsigned long long>(next - static_cast<int>(lane)));
   }
 }
 

@@ -2048,7 +2048,8 @@ static int install_pairs_impl(cvb_engine *e, int64_t nv_local, int64_t base, int
   CVB_TRY(e->d_flags.ensure(4));
   CVB_CUDA(cudaMemsetAsync(e->d_flags.p + 2, 0, sizeof(int), st));
   if (mu > 0) {
-    k_pairs_to_rows<<<grid_for(mu, 256), 256, 0, st>>>(keys, mu, base, nv_local, e->tails.p, row_count.p, e->d_flags.p + 2);
+    k_pairs_to_rows<<<static_cast<int>((mu + 255) / 256), 256, 0, st>>>(keys, mu, base, nv_local, e->tails.p, row_count.p,
+                                                                    e->d_flags.p + 2);
     e->launches++;
   }
   size_t tb5 = 0;

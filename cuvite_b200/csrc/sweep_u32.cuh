@@ -1293,21 +1293,42 @@ struct GiantTables {
   uint32_t *__restrict__ piece_key;  // [total_slots / kGiantPiece]
 };
 
+// One warp (<<<1, 32>>>): exclusive prefix sums of the chunk and table-slot counts of the listed vertices.
 __global__ void k_giant_layout(const eid_t *__restrict__ offsets, const vid_t *__restrict__ list, int n,
                                int64_t *__restrict__ chunk_start, int64_t *__restrict__ table_start) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  int64_t c = 0, s = 0;
-  for (int i = 0; i < n; ++i) {
-    chunk_start[i] = c;
-    table_start[i] = s;
-    const int64_t deg = offsets[list[i] + 1] - offsets[list[i]];
-    c += (deg + kGiantChunk - 1) / kGiantChunk;
-    int64_t cap = kGiantPiece;
-    while (2 * cap < 3 * deg) cap <<= 1;  // load factor <= 2/3 (double hashing)
-    s += cap;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const unsigned lane = threadIdx.x;
+  int64_t cbase = 0, sbase = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + static_cast<int>(lane);
+    int64_t dc = 0, ds = 0;
+    if (i < n) {
+      const int64_t deg = offsets[list[i] + 1] - offsets[list[i]];
+      dc = (deg + kGiantChunk - 1) / kGiantChunk;
+      int64_t cap = kGiantPiece;
+      while (2 * cap < 3 * deg) cap <<= 1;  // load factor <= 2/3 (double hashing)
+      ds = cap;
+    }
+    int64_t pc = dc, ps = ds;  // inclusive warp scan
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int64_t tc = __shfl_up_sync(0xffffffffu, pc, d), ts = __shfl_up_sync(0xffffffffu, ps, d);
+      if (lane >= static_cast<unsigned>(d)) {
+        pc += tc;
+        ps += ts;
+      }
+    }
+    if (i < n) {
+      chunk_start[i] = cbase + pc - dc;
+      table_start[i] = sbase + ps - ds;
+    }
+    cbase += __shfl_sync(0xffffffffu, pc, 31);
+    sbase += __shfl_sync(0xffffffffu, ps, 31);
   }
-  chunk_start[n] = c;
-  table_start[n] = s;
+  if (lane == 0) {
+    chunk_start[n] = cbase;
+    table_start[n] = sbase;
+  }
 }
 
 __global__ void k_giant_init_slots(uint2 *__restrict__ slots, int64_t n) {
